@@ -1,0 +1,509 @@
+// aggregate.cu -- fused gather - mask - scale - reduce Pi.X aggregation on B200 (sm_100a).
+//
+// Replaces, in ONE kernel and one pass over the feature rows:
+//   * the host gather `features[neighbor_idx]` + H2D copy      (/root/reference/model.py:314)
+//   * F.dropout on the Pi scores ("DropNode")                   (/root/reference/model.py:82)
+//   * feats * scores[:,None]  -- an [nz,F] temporary            (/root/reference/model.py:83)
+//   * two torch_scatter.scatter(..., reduce='sum') calls        (/root/reference/model.py:83-86)
+//   * the final divide                                          (/root/reference/model.py:87)
+// and, with eps = 1e-10 and the embedding table as `table`, MLP.emb (/root/reference/model_mag.py:48-55).
+//
+// Shape of the work: HBM-bound row gather.  One warp owns one (output row, column tile); it reads
+// the row's entry metadata coalesced (one entry per lane), draws the DropNode decisions from
+// counter-based Philox BEFORE touching the table so dropped rows cost no bandwidth, then streams
+// the kept table rows with 128-bit read-only loads, several rows in flight per lane, accumulating
+// in fp32 registers.  Rows are owned, so there are no atomics and no [nz,F] temporary; all n_aug
+// augmentations of model.py:321 share one read of every table row.  No tensor cores: this is a
+// segmented AXPY, not a dense contraction.
+#include "gp_common.cuh"
+
+#include <algorithm>
+
+namespace {
+
+constexpr int kAggBlock = 256;  // 8 warps per CTA
+constexpr int kMaxAug = 4;
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+template <int VEC>
+__device__ __forceinline__ void vec_load(float (&x)[VEC], const float *p) {
+    if constexpr (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(p));
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        x[0] = v.x; x[1] = v.y;
+    } else {
+        x[0] = __ldg(p);
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ void vec_store(float *p, const float (&x)[VEC]) {
+    if constexpr (VEC == 4) *reinterpret_cast<float4 *>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2 *>(p) = make_float2(x[0], x[1]);
+    else *p = x[0];
+}
+
+struct AggParams {
+    const float *table;
+    long long ld_table;
+    int F;
+    const int *row_ptr;
+    const int *slot_rows;
+    int slot_K;
+    const int *nbr;
+    const float *score;
+    long long B;
+    long long n_entries;
+    int use_mask;       // training && p > 0
+    float scale;        // 1/(1-p)
+    unsigned thresh;    // keep iff philox >= thresh
+    int drop_all;       // p >= 1
+    unsigned long long seed, offset;
+    const unsigned char *mask_in;
+    unsigned char *mask_out;
+    float eps;
+    float *out;
+    long long ld_out;
+    float *denom_out;
+    int n_ctile;        // column tiles per row
+    int tile_cols;      // columns per tile = NCHUNK*32*VEC
+};
+
+// Entry range of output row b.
+__device__ __forceinline__ void row_range(const AggParams &P, long long b, long long &j0, long long &j1) {
+    if (P.row_ptr) { j0 = P.row_ptr[b]; j1 = P.row_ptr[b + 1]; }
+    else {
+        const long long r = P.slot_rows ? (long long)P.slot_rows[b] : b;
+        if (r < 0) { j0 = j1 = 0; return; }  // not a GFPush source: empty row -> zeros
+        j0 = r * P.slot_K; j1 = j0 + P.slot_K;
+    }
+}
+
+// Weight of entry jj in augmentation a (0 when dropped / pad / out of range).
+__device__ __forceinline__ float entry_weight(const AggParams &P, long long jj, int a, float s, bool &keep) {
+    keep = true;
+    if (P.use_mask) {
+        if (P.mask_in) keep = P.mask_in[(long long)a * P.n_entries + jj] != 0;
+        else keep = !P.drop_all && gp_dropnode_keep((unsigned long long)jj, (unsigned)a, P.seed, P.offset, P.thresh);
+        return keep ? s * P.scale : 0.0f;
+    }
+    return s;
+}
+
+template <int VEC, int NCHUNK, int NAUG, int UNROLL>
+__global__ void __launch_bounds__(kAggBlock) aggregate_fwd_kernel(AggParams P) {
+    const int lane = gp_lane();
+    const long long warp = ((long long)blockIdx.x * kAggBlock + threadIdx.x) >> 5;
+    const long long b = warp / P.n_ctile;
+    if (b >= P.B) return;  // warp-uniform
+    const int ctile = (int)(warp - b * P.n_ctile);
+    const int col0 = ctile * P.tile_cols + lane * VEC;  // this lane's first column in chunk 0
+
+    long long j0, j1;
+    row_range(P, b, j0, j1);
+
+    float acc[NAUG][NCHUNK][VEC];
+    float wsum[NAUG];
+#pragma unroll
+    for (int a = 0; a < NAUG; a++) {
+        wsum[a] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; c++)
+#pragma unroll
+            for (int k = 0; k < VEC; k++) acc[a][c][k] = 0.0f;
+    }
+
+    for (long long j = j0; j < j1; j += 32) {
+        const long long jj = j + lane;
+        const bool valid = jj < j1;
+        int my_nbr = 0;
+        float my_m[NAUG];
+        bool any = false;
+        {
+            float s = 0.0f;
+            if (valid) {
+                s = P.score[jj];
+                my_nbr = P.nbr ? P.nbr[jj] : (int)jj;
+            }
+            const bool live = valid && (P.row_ptr != nullptr || s > 0.0f);  // slot layout: skip zero pads
+#pragma unroll
+            for (int a = 0; a < NAUG; a++) {
+                bool keep = false;
+                my_m[a] = live ? entry_weight(P, jj, a, s, keep) : 0.0f;
+                if (valid && P.mask_out && ctile == 0) P.mask_out[(long long)a * P.n_entries + jj] = (live && keep) ? 1 : 0;
+                any |= (my_m[a] != 0.0f);
+            }
+        }
+        unsigned kept = __ballot_sync(0xffffffffu, any);  // entries some augmentation keeps
+        while (kept) {
+            int src_lane[UNROLL];
+            int nb[UNROLL];
+            int cnt = 0;
+#pragma unroll
+            for (int q = 0; q < UNROLL; q++) {
+                src_lane[q] = 0;
+                if (kept) { src_lane[q] = __ffs(kept) - 1; kept &= kept - 1; cnt = q + 1; }
+                nb[q] = __shfl_sync(0xffffffffu, my_nbr, src_lane[q]);
+            }
+            float x[UNROLL][NCHUNK][VEC];
+#pragma unroll
+            for (int q = 0; q < UNROLL; q++) {
+                const float *row = P.table + (long long)nb[q] * P.ld_table;
+#pragma unroll
+                for (int c = 0; c < NCHUNK; c++) {
+                    const int col = col0 + c * 32 * VEC;
+                    if (q < cnt && col < P.F) vec_load<VEC>(x[q][c], row + col);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < VEC; k++) x[q][c][k] = 0.0f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < UNROLL; q++) {
+#pragma unroll
+                for (int a = 0; a < NAUG; a++) {
+                    float m = __shfl_sync(0xffffffffu, my_m[a], src_lane[q]);
+                    if (q >= cnt) m = 0.0f;
+                    wsum[a] += m;
+#pragma unroll
+                    for (int c = 0; c < NCHUNK; c++)
+#pragma unroll
+                        for (int k = 0; k < VEC; k++) acc[a][c][k] = fmaf(m, x[q][c][k], acc[a][c][k]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NAUG; a++) {
+        const float den = wsum[a] + P.eps;  // model.py:87 / model_mag.py:54
+        float *orow = P.out + ((long long)a * P.B + b) * P.ld_out;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; c++) {
+            const int col = col0 + c * 32 * VEC;
+            if (col < P.F) {
+                float y[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; k++) y[k] = acc[a][c][k] / den;
+                vec_store<VEC>(orow + col, y);
+            }
+        }
+        if (P.denom_out && ctile == 0 && lane == 0) P.denom_out[(long long)a * P.B + b] = den;
+    }
+}
+
+// ---------------------------------------------------------------------------------- backward
+struct AggBwdParams {
+    const float *grad_out;
+    long long ld_grad_out;
+    const float *denom;
+    const int *row_ptr;
+    const int *nbr;
+    const float *score;
+    long long B, n_entries;
+    int F;
+    int use_mask;
+    float scale;
+    const unsigned char *mask_in;
+    float *grad_table;
+    long long ld_grad_table;
+    int n_ctile, tile_cols;
+};
+
+template <int VEC>
+__device__ __forceinline__ void vec_atomic_add(float *p, const float (&x)[VEC]) {
+    if constexpr (VEC == 4) atomicAdd(reinterpret_cast<float4 *>(p), make_float4(x[0], x[1], x[2], x[3]));
+    else if constexpr (VEC == 2) atomicAdd(reinterpret_cast<float2 *>(p), make_float2(x[0], x[1]));
+    else atomicAdd(p, x[0]);
+}
+
+template <int VEC, int NCHUNK, int NAUG>
+__global__ void __launch_bounds__(kAggBlock) aggregate_bwd_kernel(AggBwdParams P) {
+    const int lane = gp_lane();
+    const long long warp = ((long long)blockIdx.x * kAggBlock + threadIdx.x) >> 5;
+    const long long b = warp / P.n_ctile;
+    if (b >= P.B) return;
+    const int ctile = (int)(warp - b * P.n_ctile);
+    const int col0 = ctile * P.tile_cols + lane * VEC;
+    const long long j0 = P.row_ptr[b], j1 = P.row_ptr[b + 1];
+
+    float g[NAUG][NCHUNK][VEC];
+#pragma unroll
+    for (int a = 0; a < NAUG; a++) {
+        const float inv = 1.0f / P.denom[(long long)a * P.B + b];
+        const float *grow = P.grad_out + ((long long)a * P.B + b) * P.ld_grad_out;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; c++) {
+            const int col = col0 + c * 32 * VEC;
+            if (col < P.F) {
+                vec_load<VEC>(g[a][c], grow + col);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) g[a][c][k] *= inv;
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) g[a][c][k] = 0.0f;
+            }
+        }
+    }
+    for (long long j = j0; j < j1; j += 32) {
+        const long long jj = j + lane;
+        const bool valid = jj < j1;
+        int my_nbr = 0;
+        float my_m[NAUG];
+        {
+            float s = 0.0f;
+            if (valid) { s = P.score[jj]; my_nbr = P.nbr ? P.nbr[jj] : 0; }
+#pragma unroll
+            for (int a = 0; a < NAUG; a++) {
+                float m = s;
+                if (P.use_mask) m = (valid && P.mask_in[(long long)a * P.n_entries + jj]) ? s * P.scale : 0.0f;
+                my_m[a] = valid ? m : 0.0f;
+            }
+        }
+        const int cnt = (int)min((long long)32, j1 - j);
+        for (int t = 0; t < cnt; t++) {
+            float m[NAUG];
+            bool any = false;
+#pragma unroll
+            for (int a = 0; a < NAUG; a++) { m[a] = __shfl_sync(0xffffffffu, my_m[a], t); any |= (m[a] != 0.0f); }
+            const int nb = __shfl_sync(0xffffffffu, my_nbr, t);
+            if (P.nbr && !any) continue;  // accumulate mode: nothing to add
+            float *drow = P.grad_table + (P.nbr ? (long long)nb : (j + t)) * P.ld_grad_table;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; c++) {
+                const int col = col0 + c * 32 * VEC;
+                if (col < P.F) {
+                    float y[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; k++) {
+                        float v = 0.0f;
+#pragma unroll
+                        for (int a = 0; a < NAUG; a++) v = fmaf(m[a], g[a][c][k], v);
+                        y[k] = v;
+                    }
+                    if (P.nbr) vec_atomic_add<VEC>(drow + col, y);
+                    else vec_store<VEC>(drow + col, y);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- small utilities
+__global__ void segments_kernel(const long long *idx, long long n, long long B, int *row_ptr, int *flags) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += stride) {
+        const long long prev = (j == 0) ? -1 : idx[j - 1];
+        const long long cur = (j == n) ? B : idx[j];
+        if (j < n && (cur < 0 || cur >= B)) { atomicOr(flags, 1); continue; }
+        if (cur < prev) { atomicOr(flags, 1); continue; }
+        for (long long r = max(prev, -1ll) + 1; r <= min(cur, B); r++) row_ptr[r] = (int)j;  // rows prev+1..cur start at j
+    }
+}
+
+__global__ void narrow_kernel(const long long *idx, long long n, long long n_rows, int *out, int *flags) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const long long v = idx[j];
+        if (v < 0 || v >= n_rows) atomicOr(flags, 1);
+        out[j] = (int)v;
+    }
+}
+
+__global__ void mask_kernel(long long n, int n_aug, unsigned thresh, int drop_all, unsigned long long seed,
+                            unsigned long long offset, unsigned char *mask) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        for (int a = 0; a < n_aug; a++)
+            mask[(long long)a * n + j] = (!drop_all && gp_dropnode_keep((unsigned long long)j, (unsigned)a, seed, offset, thresh)) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------- dispatch
+struct Tiling { int vec, nchunk, n_ctile, tile_cols; };
+
+bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// Widest vector the row starts allow, then the fewest column tiles of <= 4 chunks per lane.
+Tiling choose_tiling(int F, const void *p0, long long ld0, const void *p1, long long ld1) {
+    int vec = 4;
+    while (vec > 1) {
+        const size_t bytes = (size_t)vec * 4;
+        if (aligned_to(p0, bytes) && aligned_to(p1, bytes) && ld0 % vec == 0 && ld1 % vec == 0) break;
+        vec >>= 1;
+    }
+    while (vec > 1 && 32 * (vec / 2) >= F) vec >>= 1;  // narrow rows: keep all 32 lanes busy
+    const int chunks = (F + 32 * vec - 1) / (32 * vec);
+    const int n_ctile = (chunks + 3) / 4;
+    const int nchunk = (chunks + n_ctile - 1) / n_ctile;
+    return Tiling{vec, nchunk, n_ctile, nchunk * 32 * vec};
+}
+
+template <int VEC, int NCHUNK, int NAUG>
+int launch_fwd_t(const AggParams &P, cudaStream_t stream) {
+    constexpr int UNROLL = NCHUNK == 1 ? 8 : NCHUNK == 2 ? 4 : 2;
+    const long long warps = P.B * P.n_ctile;
+    const long long blocks = (warps * 32 + kAggBlock - 1) / kAggBlock;
+    GP_REQUIRE(blocks < (1ll << 31), "batch too large for one launch");
+    aggregate_fwd_kernel<VEC, NCHUNK, NAUG, UNROLL><<<(unsigned)blocks, kAggBlock, 0, stream>>>(P);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+template <int VEC, int NCHUNK>
+int launch_fwd_a(const AggParams &P, int n_aug, cudaStream_t s) {
+    switch (n_aug) {
+        case 1: return launch_fwd_t<VEC, NCHUNK, 1>(P, s);
+        case 2: return launch_fwd_t<VEC, NCHUNK, 2>(P, s);
+        case 3: return launch_fwd_t<VEC, NCHUNK, 3>(P, s);
+        default: return launch_fwd_t<VEC, NCHUNK, 4>(P, s);
+    }
+}
+
+template <int VEC>
+int launch_fwd_c(const AggParams &P, int nchunk, int n_aug, cudaStream_t s) {
+    switch (nchunk) {
+        case 1: return launch_fwd_a<VEC, 1>(P, n_aug, s);
+        case 2: return launch_fwd_a<VEC, 2>(P, n_aug, s);
+        case 3: return launch_fwd_a<VEC, 3>(P, n_aug, s);
+        default: return launch_fwd_a<VEC, 4>(P, n_aug, s);
+    }
+}
+
+template <int VEC, int NCHUNK, int NAUG>
+int launch_bwd_t(const AggBwdParams &P, cudaStream_t stream) {
+    const long long warps = P.B * P.n_ctile;
+    const long long blocks = (warps * 32 + kAggBlock - 1) / kAggBlock;
+    GP_REQUIRE(blocks < (1ll << 31), "batch too large for one launch");
+    aggregate_bwd_kernel<VEC, NCHUNK, NAUG><<<(unsigned)blocks, kAggBlock, 0, stream>>>(P);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+template <int VEC, int NCHUNK>
+int launch_bwd_a(const AggBwdParams &P, int n_aug, cudaStream_t s) {
+    switch (n_aug) {
+        case 1: return launch_bwd_t<VEC, NCHUNK, 1>(P, s);
+        case 2: return launch_bwd_t<VEC, NCHUNK, 2>(P, s);
+        case 3: return launch_bwd_t<VEC, NCHUNK, 3>(P, s);
+        default: return launch_bwd_t<VEC, NCHUNK, 4>(P, s);
+    }
+}
+
+template <int VEC>
+int launch_bwd_c(const AggBwdParams &P, int nchunk, int n_aug, cudaStream_t s) {
+    switch (nchunk) {
+        case 1: return launch_bwd_a<VEC, 1>(P, n_aug, s);
+        case 2: return launch_bwd_a<VEC, 2>(P, n_aug, s);
+        case 3: return launch_bwd_a<VEC, 3>(P, n_aug, s);
+        default: return launch_bwd_a<VEC, 4>(P, n_aug, s);
+    }
+}
+
+void dropout_consts(double p, int training, int *use_mask, float *scale, unsigned *thresh, int *drop_all) {
+    *use_mask = (training && p > 0.0) ? 1 : 0;
+    *drop_all = (p >= 1.0) ? 1 : 0;
+    // ATen: noise = bernoulli(1-p) / (1-p) with the python-float p narrowed to fp32 (Dropout.cpp)
+    *scale = *drop_all ? 0.0f : 1.0f / (float)(1.0 - p);
+    *thresh = gp_keep_threshold((float)p);
+}
+
+}  // namespace
+
+extern "C" {
+
+int gp_aggregate_fwd(const gp_aggregate_args *A, void *stream) {
+    GP_REQUIRE(A != nullptr, "args is null");
+    GP_REQUIRE(A->B >= 0 && A->n_entries >= 0, "negative size");
+    GP_REQUIRE(A->F >= 1, "F must be >= 1");
+    GP_REQUIRE(A->n_aug >= 1 && A->n_aug <= kMaxAug, "n_aug must be in 1..%d", kMaxAug);
+    GP_REQUIRE(A->p >= 0.0 && A->p <= 1.0, "dropnode rate must be in [0,1]");
+    if (A->B == 0) return GP_OK;
+    GP_REQUIRE(A->table && A->score && A->out, "null device buffer");
+    GP_REQUIRE(A->ld_table >= A->F && A->ld_out >= A->F, "row stride smaller than F");
+    GP_REQUIRE(A->row_ptr != nullptr || A->slot_K >= 1, "slot layout needs slot_K >= 1");
+    GP_REQUIRE(A->n_entries < (1ll << 31), "entry count exceeds int32 (split the batch)");
+    GP_REQUIRE(gp_device_count() > 0, "no CUDA device: this library has no CPU fallback");
+    AggParams P{};
+    P.table = A->table; P.ld_table = A->ld_table; P.F = A->F;
+    P.row_ptr = A->row_ptr; P.slot_rows = A->slot_rows; P.slot_K = A->slot_K;
+    P.nbr = A->nbr; P.score = A->score; P.B = A->B; P.n_entries = A->n_entries;
+    dropout_consts(A->p, A->training, &P.use_mask, &P.scale, &P.thresh, &P.drop_all);
+    P.seed = A->seed; P.offset = A->offset;
+    P.mask_in = A->mask_in; P.mask_out = A->mask_out; P.eps = A->eps;
+    P.out = A->out; P.ld_out = A->ld_out; P.denom_out = A->denom_out;
+    const Tiling t = choose_tiling(A->F, A->table, A->ld_table, A->out, A->ld_out);
+    P.n_ctile = t.n_ctile; P.tile_cols = t.tile_cols;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (t.vec) {
+        case 4: return launch_fwd_c<4>(P, t.nchunk, A->n_aug, s);
+        case 2: return launch_fwd_c<2>(P, t.nchunk, A->n_aug, s);
+        default: return launch_fwd_c<1>(P, t.nchunk, A->n_aug, s);
+    }
+}
+
+int gp_aggregate_bwd(const gp_aggregate_bwd_args *A, void *stream) {
+    GP_REQUIRE(A != nullptr, "args is null");
+    GP_REQUIRE(A->B >= 0 && A->n_entries >= 0, "negative size");
+    GP_REQUIRE(A->F >= 1, "F must be >= 1");
+    GP_REQUIRE(A->n_aug >= 1 && A->n_aug <= kMaxAug, "n_aug must be in 1..%d", kMaxAug);
+    if (A->B == 0) return GP_OK;
+    GP_REQUIRE(A->grad_out && A->denom && A->row_ptr && A->score && A->grad_table, "null device buffer");
+    GP_REQUIRE(A->ld_grad_out >= A->F && A->ld_grad_table >= A->F, "row stride smaller than F");
+    GP_REQUIRE(gp_device_count() > 0, "no CUDA device: this library has no CPU fallback");
+    AggBwdParams P{};
+    P.grad_out = A->grad_out; P.ld_grad_out = A->ld_grad_out; P.denom = A->denom;
+    P.row_ptr = A->row_ptr; P.nbr = A->nbr; P.score = A->score; P.B = A->B; P.n_entries = A->n_entries; P.F = A->F;
+    unsigned thresh; int drop_all;
+    dropout_consts(A->p, A->training, &P.use_mask, &P.scale, &thresh, &drop_all);
+    GP_REQUIRE(!P.use_mask || A->mask_in, "training-mode backward needs the forward pass's mask");
+    P.mask_in = A->mask_in; P.grad_table = A->grad_table; P.ld_grad_table = A->ld_grad_table;
+    const Tiling t = choose_tiling(A->F, A->grad_out, A->ld_grad_out, A->grad_table, A->ld_grad_table);
+    P.n_ctile = t.n_ctile; P.tile_cols = t.tile_cols;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (t.vec) {
+        case 4: return launch_bwd_c<4>(P, t.nchunk, A->n_aug, s);
+        case 2: return launch_bwd_c<2>(P, t.nchunk, A->n_aug, s);
+        default: return launch_bwd_c<1>(P, t.nchunk, A->n_aug, s);
+    }
+}
+
+int gp_segments_from_sorted_index(const int64_t *d_idx, int64_t n, int64_t B, int32_t *d_row_ptr, int32_t *d_flags,
+                                  void *stream) {
+    GP_REQUIRE(n >= 0 && B >= 0 && n < (1ll << 31), "bad sizes");
+    GP_REQUIRE(d_row_ptr && d_flags && (d_idx || n == 0), "null device buffer");
+    const long long blocks = std::min<long long>((n + 1 + 255) / 256, 148 * 8);
+    segments_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const long long *)d_idx, n, B, d_row_ptr, d_flags);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+int gp_narrow_index(const int64_t *d_idx, int64_t n, int64_t n_rows, int32_t *d_out, int32_t *d_flags, void *stream) {
+    GP_REQUIRE(n >= 0 && n_rows >= 0 && n_rows < (1ll << 31), "bad sizes");
+    if (n == 0) return GP_OK;
+    GP_REQUIRE(d_idx && d_out && d_flags, "null device buffer");
+    const long long blocks = std::min<long long>((n + 255) / 256, 148 * 8);
+    narrow_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const long long *)d_idx, n, n_rows, d_out, d_flags);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, uint64_t offset, uint8_t *d_mask,
+                     void *stream) {
+    GP_REQUIRE(n_entries >= 0 && n_aug >= 1 && n_aug <= kMaxAug, "bad sizes");
+    GP_REQUIRE(p >= 0.0 && p <= 1.0, "dropnode rate must be in [0,1]");
+    if (n_entries == 0) return GP_OK;
+    GP_REQUIRE(d_mask != nullptr, "null device buffer");
+    const long long blocks = std::min<long long>((n_entries + 255) / 256, 148 * 8);
+    mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(n_entries, n_aug, gp_keep_threshold((float)p),
+                                                                   p >= 1.0 ? 1 : 0, seed, offset, d_mask);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,749 @@
+// gfpush.cu -- GFPush + top-k on B200 (sm_100a).  Replaces Graph::gfpush_omp,
+// /root/reference/precompute/graph.h:53-131 (bound at precompute/propagation.cpp:8-12).
+//
+// Algorithm (what the reference computes, restated in SURVEY.md 3.2 / oracle/gfpush_oracle.c):
+//   per source s:  r^0 = e_s;  for i < L-1:  reserve += coef[i] r^i ;
+//                  r^{i+1}[v] = sum_{u in N^-1(v), r^i[u] >= rmax deg(u)} r^i[u]/deg(u)  (+ dangling -> s)
+//                  reserve += coef[L-1] r^{L-1};  keep the top-K positive reserve entries.
+//
+// B200 design (not the reference's per-thread unordered_maps):
+//   * persistent CTAs (SM count x resident CTAs), sources handed out through one global atomic
+//     counter -- the schedule(dynamic) of graph.h:73, so hub-heavy sources do not stall a wave;
+//   * per-CTA DIRECT-ADDRESSED tables instead of hash maps: `nxt[n]` (next-level residue, fp64,
+//     accumulated with native fp64 atomics) and `rsv[n]` (reserve, fp64).  180 GB of HBM makes a
+//     perfect hash (node id -> slot) affordable for every BASELINE config, which removes all
+//     probing; small graphs put `nxt` in shared memory instead (scratch mode SMEM);
+//   * frontiers are compact (id, value) lists; a node joins the next frontier when its atomicAdd
+//     returns 0.0 (first touch), so tables are cleared by walking lists, never by memset;
+//   * edge-balanced expansion: a CTA tile of BLOCK frontier nodes is prefix-summed by degree and
+//     the tile's edges are dealt to threads by rank, so a 240K-degree hub is expanded by the whole
+//     CTA with coalesced `indices` reads and degree-1 leaves do not idle a warp each;
+//   * top-k is an MSD radix select on the fp64 bit pattern (11-bit digits, exponent first),
+//     finished by rank-counting the single boundary bucket in shared memory.
+//   Residues stay fp64 end to end (the threshold test r >= rmax*deg is a hard comparison).
+#include "gp_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <mutex>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int kHistBins = 2048;     // 11-bit radix digits
+constexpr int kBucketCap = 512;     // boundary bucket resolved in shared memory
+constexpr int kMaxK = kBucketCap;   // K above this is refused
+constexpr int kMaxLevels = 256;
+constexpr unsigned long long kUnseen = ~0ull;  // rsv sentinel: bit pattern of a NaN no sum can produce
+constexpr int kEdgeUnroll = 4;
+
+struct PushParams {
+    const int *indptr;
+    const int *indices;
+    int n;
+    const int *node_idx;
+    long long S;
+    const double *coef;  // device [L]
+    int L;
+    double rmax;
+    int K;
+    int *out_row;
+    int *out_col;
+    double *out_val;
+    float *out_val32;  // nullable
+    // per-CTA scratch
+    double *nxt_slab;  // [ctas][n]   (HBM mode; unused in SMEM mode)
+    double *rsv_slab;  // [ctas][n]   all words == kUnseen between sources
+    int *cur_id;       // [ctas][capF]
+    double *cur_val;   // [ctas][capF]
+    int *nxt_id;       // [ctas][capF]
+    int *sup_id;       // [ctas][capS]
+    double *cand_val;  // [ctas][capS]
+    long long capF, capS;
+    unsigned long long *queue;  // [1] next source
+    unsigned long long *stats;  // [0] edges [1] frontier [2] support [3] error flags
+};
+
+enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
+
+template <int BLOCK>
+struct PushSmem {
+    unsigned off[BLOCK];
+    int start[BLOCK];
+    double val[BLOCK];
+    unsigned warp_scan[BLOCK / 32 + 1];
+    unsigned hist[kHistBins];
+    unsigned long long bkey[kBucketCap];
+    int bid[kBucketCap];
+    long long it;
+    int n_cur, n_nxt, n_sup, n_out, n_bucket;
+    int sel_bin, sel_above, sel_inbin;
+};
+
+__device__ __forceinline__ double atomic_add_ret(double *p, double v) { return atomicAdd(p, v); }
+
+// Append ids flagged by `is_new` to list[0..cap) through one shared counter per warp.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_append(bool is_new, int id, int *list, long long cap, int *s_count,
+                                            unsigned long long *err) {
+    const unsigned m = __ballot_sync(0xffffffffu, is_new);
+    if (m == 0) return;
+    const int lane = gp_lane();
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(s_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (is_new) {
+        long long pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < cap) list[pos] = id;
+        else atomicOr(err, kErrOverflow);
+    }
+}
+
+// Largest t in [0, BLOCK) with off[t] <= e (off is a non-decreasing exclusive scan, off[0] == 0).
+template <int BLOCK>
+__device__ __forceinline__ int owner_of_edge(const unsigned *off, unsigned e) {
+    int lo = 0, hi = BLOCK;  // invariant: off[lo] <= e, (hi == BLOCK or off[hi] > e)
+#pragma unroll
+    for (int step = BLOCK / 2; step >= 1; step >>= 1) {
+        int mid = lo + step;
+        if (mid < hi && off[mid] <= e) lo = mid;
+    }
+    return lo;
+}
+
+// Finds the radix bin holding the kk-th largest among `hist` (bins ordered ascending by key).
+// Results in sm.sel_bin / sel_above (count in strictly higher bins) / sel_inbin; returns total.
+template <int BLOCK>
+__device__ __forceinline__ unsigned select_bin(PushSmem<BLOCK> &sm, int nbins, int kk, bool kk_is_cap) {
+    // thread t owns bins [hi - per + 1, hi], hi = nbins-1 - t*per, walking from the top
+    const int per = (nbins + BLOCK - 1) / BLOCK;
+    const int tid = threadIdx.x;
+    unsigned local = 0;
+    const int hi = nbins - 1 - tid * per;
+#pragma unroll 4
+    for (int i = 0; i < per; i++) {
+        int b = hi - i;
+        if (b >= 0) local += sm.hist[b];
+    }
+    unsigned total;
+    unsigned above = gp_block_exclusive_scan<BLOCK>(local, sm.warp_scan, total);
+    unsigned want = kk_is_cap ? min((unsigned)kk, total) : (unsigned)kk;
+    if (want > 0 && above < want && want <= above + local) {
+        unsigned acc = above;
+        for (int i = 0; i < per; i++) {
+            int b = hi - i;
+            if (b < 0) break;
+            unsigned h = sm.hist[b];
+            if (acc + h >= want) { sm.sel_bin = b; sm.sel_above = (int)acc; sm.sel_inbin = (int)h; break; }
+            acc += h;
+        }
+    }
+    if (want == 0 && tid == 0) { sm.sel_bin = -1; sm.sel_above = 0; sm.sel_inbin = 0; }
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ void emit(const PushParams &P, long long it, int src, int slot, int col, double v) {
+    long long o = it * P.K + slot;
+    P.out_row[o] = src;
+    P.out_col[o] = col;
+    P.out_val[o] = v;
+    if (P.out_val32) P.out_val32[o] = (float)v;
+}
+
+template <int BLOCK, bool SMEM_NXT>
+__global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
+    __shared__ PushSmem<BLOCK> sm;
+    extern __shared__ double s_nxt_dyn[];
+
+    const int tid = threadIdx.x;
+    const int lane = gp_lane();
+    const long long cta = blockIdx.x;
+    double *nxt = SMEM_NXT ? s_nxt_dyn : P.nxt_slab + cta * (long long)P.n;
+    double *rsv = P.rsv_slab + cta * (long long)P.n;
+    int *cur_id = P.cur_id + cta * P.capF;
+    double *cur_val = P.cur_val + cta * P.capF;
+    int *nxt_id = P.nxt_id + cta * P.capF;
+    int *sup_id = P.sup_id + cta * P.capS;
+    double *cand_val = P.cand_val + cta * P.capS;
+    unsigned long long *err = P.stats + 3;
+
+    if (SMEM_NXT) {
+        for (int i = tid; i < P.n; i += BLOCK) nxt[i] = 0.0;
+    }
+    unsigned long long st_edges = 0, st_frontier = 0, st_support = 0;  // thread 0 only
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            sm.it = (long long)atomicAdd(P.queue, 1ull);
+            sm.n_cur = 1; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0;
+        }
+        __syncthreads();
+        const long long it = sm.it;
+        if (it >= P.S) break;
+        const int src = P.node_idx[it];
+        if (src < 0 || src >= P.n) {  // refuse instead of reading out of bounds
+            if (tid == 0) atomicOr(err, kErrBadSource);
+            for (int i = tid; i < P.K; i += BLOCK) emit(P, it, 0, i, 0, 0.0);
+            continue;
+        }
+        if (tid == 0) { cur_id[0] = src; cur_val[0] = 1.0; }  // graph.h:80
+        __syncthreads();
+
+        // ------------------------------------------------------------------ push levels
+        for (int level = 0; level < P.L - 1; level++) {  // graph.h:83
+            const int n_cur = sm.n_cur;
+            const double c = P.coef[level];
+            if (tid == 0) st_frontier += n_cur;
+            for (int base = 0; base < n_cur; base += BLOCK) {
+                const int j = base + tid;
+                unsigned d_push = 0;
+                int start = 0;
+                double val = 0.0;
+                bool new_sup = false;
+                int u = 0;
+                bool dangling = false;
+                double r = 0.0;
+                if (j < n_cur) {
+                    u = cur_id[j];
+                    r = cur_val[j];
+                    double old = rsv[u];
+                    if (__double_as_longlong(old) == (long long)kUnseen) { old = 0.0; new_sup = true; }
+                    rsv[u] = old + c * r;  // graph.h:90 (credited before the threshold test)
+                    const int a = P.indptr[u], b = P.indptr[u + 1];
+                    const unsigned d = (unsigned)(b - a);
+                    if (d == 0) dangling = true;            // graph.h:91-93
+                    else if (r >= P.rmax * (double)d) {     // graph.h:94
+                        d_push = d; start = a; val = r / (double)d;  // graph.h:95
+                    }
+                }
+                warp_append(new_sup, u, sup_id, P.capS, &sm.n_sup, err);
+                {
+                    bool is_new = false;
+                    if (dangling) is_new = (atomic_add_ret(&nxt[src], r) == 0.0);
+                    warp_append(is_new, src, nxt_id, P.capF, &sm.n_nxt, err);
+                }
+                unsigned total;
+                const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
+                sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
+                __syncthreads();
+                if (tid == 0) st_edges += total;
+                // edges of the tile, dealt by rank: warp w takes chunks of 32*kEdgeUnroll edges
+                for (unsigned e0 = (unsigned)(tid >> 5) * (32u * kEdgeUnroll); e0 < total;
+                     e0 += (BLOCK / 32) * (32u * kEdgeUnroll)) {
+                    int v[kEdgeUnroll];
+                    double add[kEdgeUnroll];
+                    bool ok[kEdgeUnroll];
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        const unsigned e = e0 + q * 32u + lane;
+                        ok[q] = e < total;
+                        v[q] = 0; add[q] = 0.0;
+                        if (ok[q]) {
+                            const int t = owner_of_edge<BLOCK>(sm.off, e);
+                            v[q] = __ldg(P.indices + sm.start[t] + (e - sm.off[t]));  // graph.h:96-97
+                            add[q] = sm.val[t];
+                        }
+                    }
+                    bool fresh[kEdgeUnroll];
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++)
+                        fresh[q] = ok[q] && (atomic_add_ret(&nxt[v[q]], add[q]) == 0.0);  // graph.h:98
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++)
+                        warp_append(fresh[q], v[q], nxt_id, P.capF, &sm.n_nxt, err);
+                }
+                __syncthreads();
+            }
+            // residue = next (graph.h:102): drain the table through the id list, leaving it zeroed
+            const int n_nxt = min((long long)sm.n_nxt, P.capF);
+            for (int j = tid; j < n_nxt; j += BLOCK) {
+                const int v = nxt_id[j];
+                double x;
+                if (SMEM_NXT) { x = nxt[v]; nxt[v] = 0.0; }
+                else x = __longlong_as_double((long long)atomicExch((unsigned long long *)&nxt[v], 0ull));
+                cur_id[j] = v;
+                cur_val[j] = x;
+            }
+            __syncthreads();
+            if (tid == 0) { sm.n_cur = n_nxt; sm.n_nxt = 0; }
+            __syncthreads();
+        }
+        // ------------------------------------------------------------------ last level, graph.h:104-110
+        {
+            const int n_cur = sm.n_cur;
+            const double c = P.coef[P.L - 1];
+            if (tid == 0) st_frontier += n_cur;
+            for (int base = 0; base < n_cur; base += BLOCK) {
+                const int j = base + tid;
+                bool new_sup = false;
+                int u = 0;
+                if (j < n_cur) {
+                    u = cur_id[j];
+                    double old = rsv[u];
+                    if (__double_as_longlong(old) == (long long)kUnseen) { old = 0.0; new_sup = true; }
+                    rsv[u] = old + c * cur_val[j];
+                }
+                warp_append(new_sup, u, sup_id, P.capS, &sm.n_sup, err);
+            }
+        }
+        for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
+        __syncthreads();
+
+        // ------------------------------------------------------------------ top-k, graph.h:111-126
+        const int n_sup = min((long long)sm.n_sup, P.capS);
+        if (tid == 0) st_support += n_sup;
+        // pass 0: move the reserve out of the table (restoring the sentinel) + exponent histogram
+        for (int j = tid; j < n_sup; j += BLOCK) {
+            const int u = sup_id[j];
+            const double x = rsv[u];
+            reinterpret_cast<unsigned long long *>(rsv)[u] = kUnseen;
+            cand_val[j] = x;
+            if (x > 0.0) atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u);
+        }
+        __syncthreads();
+        int shift = 52, bits = 11;
+        unsigned long long prefix = 0;  // value of key >> (shift+bits) shared by the boundary bucket
+        int kk = P.K;
+        bool first = true;
+        int n_above_total = 0;
+        unsigned long long T = 0;
+        int want_bucket = 0;
+        for (;;) {
+            const unsigned total = select_bin<BLOCK>(sm, 1 << bits, kk, first);
+            if (first) kk = min(kk, (int)total);  // k = min(K, #positive): graph.h:113 + the v>0 filter of :121
+            if (kk == 0) { want_bucket = 0; T = ~0ull; break; }
+            const int bin = sm.sel_bin, above = sm.sel_above, inbin = sm.sel_inbin;
+            T = (prefix << bits) | (unsigned long long)bin;
+            n_above_total += above;
+            want_bucket = kk - above;
+            if (inbin <= kBucketCap || shift == 0) break;
+            // refine inside the boundary bucket on the next digit
+            kk = want_bucket; first = false; prefix = T;
+            __syncthreads();
+            for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
+            __syncthreads();
+            const int nshift = shift >= 11 ? shift - 11 : 0;
+            const int nbits = shift >= 11 ? 11 : shift;
+            for (int j = tid; j < n_sup; j += BLOCK) {
+                const double x = cand_val[j];
+                if (x > 0.0) {
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+                    if ((key >> shift) == prefix)
+                        atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
+                }
+            }
+            shift = nshift; bits = nbits;
+            __syncthreads();
+        }
+        // final pass: everything above the boundary bucket is selected; the bucket goes to smem
+        for (int j = tid; j < n_sup; j += BLOCK) {
+            const double x = cand_val[j];
+            if (x > 0.0) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+                const unsigned long long t = key >> shift;
+                if (t > T) {
+                    emit(P, it, src, atomicAdd(&sm.n_out, 1), sup_id[j], x);
+                } else if (t == T) {
+                    const int pos = atomicAdd(&sm.n_bucket, 1);
+                    if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = sup_id[j]; }
+                }
+            }
+        }
+        __syncthreads();
+        {
+            // rank-count the boundary bucket: keep its `want_bucket` largest (ties: lower slot first)
+            const int nb = min(sm.n_bucket, kBucketCap);
+            for (int i = tid; i < nb; i += BLOCK) {
+                const unsigned long long ki = sm.bkey[i];
+                int rank = 0;
+                for (int q = 0; q < nb; q++) {
+                    const unsigned long long kq = sm.bkey[q];
+                    rank += (kq > ki) || (kq == ki && q < i);
+                }
+                if (rank < want_bucket)
+                    emit(P, it, src, atomicAdd(&sm.n_out, 1), sm.bid[i], __longlong_as_double((long long)ki));
+            }
+        }
+        __syncthreads();
+        // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
+        for (int i = sm.n_out + tid; i < P.K; i += BLOCK) emit(P, it, 0, i, 0, 0.0);
+        (void)n_above_total;
+    }
+    if (tid == 0) {
+        atomicAdd(P.stats + 0, st_edges);
+        atomicAdd(P.stats + 1, st_frontier);
+        atomicAdd(P.stats + 2, st_support);
+    }
+}
+
+// CSR sanity: indptr[0]==0, non-decreasing, indptr[n]==nnz, 0 <= indices < n.
+__global__ void validate_csr_kernel(const int *indptr, long long n, const int *indices, long long nnz, int *flag) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int bad = 0;
+    for (long long i = i0; i < n; i += stride) bad |= (indptr[i + 1] < indptr[i]);
+    for (long long i = i0; i < nnz; i += stride) bad |= (indices[i] < 0 || indices[i] >= n);
+    if (i0 == 0) bad |= (indptr[0] != 0) | ((long long)indptr[n] != nnz);
+    if (bad) atomicOr(flag, 1);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+struct gp_graph {
+    int device = 0;
+    long long n = 0, nnz = 0;
+    int *d_indptr = nullptr;
+    int *d_indices = nullptr;
+    bool owns_csr = false;
+    int num_sms = GP_NUM_SMS_FALLBACK;
+    size_t smem_optin = 0;
+    gp_push_config cfg{};
+    cudaStream_t stream = nullptr;
+    // scratch (lazily sized for the most demanding call so far)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
+    int scratch_mode = 0;
+    double *d_coef = nullptr;              // [kMaxLevels]
+    unsigned long long *d_ctrl = nullptr;  // [0] queue, [1..4] stats
+    // staging for the host-buffer entry point
+    int *d_node = nullptr;
+    size_t d_node_cap = 0;
+    void *d_out = nullptr;
+    size_t d_out_cap = 0;
+    gp_push_stats last{};
+    std::mutex mu;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <int BLOCK>
+size_t static_smem_bytes() { return sizeof(PushSmem<BLOCK>); }
+
+struct Plan {
+    int block;
+    int mode;  // GP_SCRATCH_SMEM / GP_SCRATCH_HBM
+    long long ctas, capF, capS;
+    size_t dyn_smem;
+    size_t bytes;
+    size_t off_nxt, off_rsv, off_cur_id, off_cur_val, off_nxt_id, off_sup_id, off_cand;
+};
+
+int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
+    const long long n = g->n;
+    int block = g->cfg.block_threads ? g->cfg.block_threads : 512;
+    GP_REQUIRE(block == 256 || block == 512 || block == 1024, "block_threads must be 256, 512 or 1024 (got %d)", block);
+    const size_t stat = block == 256 ? static_smem_bytes<256>() : block == 512 ? static_smem_bytes<512>() : static_smem_bytes<1024>();
+    const size_t smem_need = stat + (size_t)n * sizeof(double) + 1024;
+    int mode = g->cfg.scratch_mode;
+    if (mode == GP_SCRATCH_AUTO) mode = (smem_need <= g->smem_optin) ? GP_SCRATCH_SMEM : GP_SCRATCH_HBM;
+    GP_REQUIRE(mode == GP_SCRATCH_SMEM || mode == GP_SCRATCH_HBM, "unknown scratch_mode %d", mode);
+    GP_REQUIRE(mode != GP_SCRATCH_SMEM || smem_need <= g->smem_optin,
+               "GP_SCRATCH_SMEM needs %zu B of shared memory, device offers %zu", smem_need, g->smem_optin);
+    // SURVEY 7 work bound: each pushed edge carries >= rmax of a level's <= 1 total mass, so a
+    // level creates at most 1/rmax frontier entries (+1 for the dangling return to the source).
+    long long capF = n;
+    if (rmax > 0.0) {
+        double b = std::ceil(1.0 / rmax * 1.0001) + 16.0;
+        if (b < (double)n) capF = (long long)b;
+    }
+    long long capS = n;
+    {
+        double b = 1.0 + (double)std::max(L - 1, 0) * (double)capF + 16.0;
+        if (b < (double)n) capS = (long long)b;
+    }
+    capF = std::max<long long>(capF, 1);
+    capS = std::max<long long>(capS, 1);
+    int per_sm = g->cfg.ctas_per_sm;
+    if (per_sm <= 0) per_sm = std::max(1, 2048 / block / 2);  // half the thread slots: 2 x 512
+    if (mode == GP_SCRATCH_SMEM) {
+        const int fit = std::max(1, (int)(((size_t)228 * 1024) / smem_need));  // 228 KB of smem per SM
+        per_sm = std::min(per_sm, fit);
+    }
+    long long ctas = std::min<long long>((long long)g->num_sms * per_sm, std::max<long long>(S, 1));
+    auto bytes_for = [&](long long c, Plan *p) {
+        size_t o = 0;
+        p->off_nxt = o; if (mode == GP_SCRATCH_HBM) o += align_up((size_t)c * n * 8, 256);
+        p->off_rsv = o; o += align_up((size_t)c * n * 8, 256);
+        p->off_cur_id = o; o += align_up((size_t)c * capF * 4, 256);
+        p->off_cur_val = o; o += align_up((size_t)c * capF * 8, 256);
+        p->off_nxt_id = o; o += align_up((size_t)c * capF * 4, 256);
+        p->off_sup_id = o; o += align_up((size_t)c * capS * 4, 256);
+        p->off_cand = o; o += align_up((size_t)c * capS * 8, 256);
+        return o;
+    };
+    size_t budget = (size_t)g->cfg.max_scratch_bytes;
+    if (budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        GP_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        budget = (free_b + g->scratch_bytes) / 2;
+    }
+    Plan tmp{};
+    while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
+    pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
+    pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : 0;
+    pl->bytes = bytes_for(ctas, pl);
+    GP_REQUIRE(pl->bytes <= budget || ctas == 1, "scratch does not fit the budget");
+    return GP_OK;
+}
+
+int ensure_scratch(gp_graph *g, const Plan &pl, cudaStream_t stream) {
+    const bool same = g->scratch && g->scratch_bytes >= pl.bytes && g->scratch_ctas == pl.ctas &&
+                      g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode;
+    if (same) return GP_OK;
+    if (g->scratch && g->scratch_bytes < pl.bytes) {
+        GP_CUDA_TRY(cudaStreamSynchronize(stream));
+        GP_CUDA_TRY(cudaFree(g->scratch));
+        g->scratch = nullptr; g->scratch_bytes = 0;
+    }
+    if (!g->scratch) {
+        GP_CUDA_TRY(cudaMalloc(&g->scratch, pl.bytes));
+        g->scratch_bytes = pl.bytes;
+    }
+    // table invariants between sources: nxt == 0 everywhere, rsv == kUnseen everywhere
+    char *base = (char *)g->scratch;
+    if (pl.mode == GP_SCRATCH_HBM)
+        GP_CUDA_TRY(cudaMemsetAsync(base + pl.off_nxt, 0, (size_t)pl.ctas * g->n * 8, stream));
+    GP_CUDA_TRY(cudaMemsetAsync(base + pl.off_rsv, 0xFF, (size_t)pl.ctas * g->n * 8, stream));
+    g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
+    return GP_OK;
+}
+
+template <int BLOCK>
+int launch_push(const PushParams &P, const Plan &pl, cudaStream_t stream) {
+    if (pl.mode == GP_SCRATCH_SMEM) {
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pl.dyn_smem));
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+        gfpush_kernel<BLOCK, true><<<(unsigned)pl.ctas, BLOCK, pl.dyn_smem, stream>>>(P);
+    } else {
+        gfpush_kernel<BLOCK, false><<<(unsigned)pl.ctas, BLOCK, 0, stream>>>(P);
+    }
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const double *coef, int L, double rmax,
+                       int K, int *d_row, int *d_col, double *d_val, float *d_val32, cudaStream_t stream) {
+    GP_REQUIRE(S >= 0, "negative source count");
+    GP_REQUIRE(L >= 1 && L <= kMaxLevels, "coef must have 1..%d entries (got %d)", kMaxLevels, L);
+    GP_REQUIRE(K >= 1 && K <= kMaxK, "top_k must be in 1..%d (got %d)", kMaxK, K);
+    GP_REQUIRE(coef != nullptr, "coef is null");
+    GP_REQUIRE(!(rmax != rmax), "rmax is NaN");
+    g->last = gp_push_stats{};
+    if (S == 0) return GP_OK;
+    GP_REQUIRE(d_node_idx && d_row && d_col && d_val, "null device buffer");
+    Plan pl{};
+    int rc = make_plan(g, S, L, rmax, &pl);
+    if (rc != GP_OK) return rc;
+    rc = ensure_scratch(g, pl, stream);
+    if (rc != GP_OK) return rc;
+    GP_CUDA_TRY(cudaMemcpyAsync(g->d_coef, coef, sizeof(double) * L, cudaMemcpyHostToDevice, stream));
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 8, stream));
+    char *base = (char *)g->scratch;
+    PushParams P{};
+    P.indptr = g->d_indptr; P.indices = g->d_indices; P.n = (int)g->n;
+    P.node_idx = d_node_idx; P.S = S; P.coef = g->d_coef; P.L = L; P.rmax = rmax; P.K = K;
+    P.out_row = d_row; P.out_col = d_col; P.out_val = d_val; P.out_val32 = d_val32;
+    P.nxt_slab = (double *)(base + pl.off_nxt);
+    P.rsv_slab = (double *)(base + pl.off_rsv);
+    P.cur_id = (int *)(base + pl.off_cur_id);
+    P.cur_val = (double *)(base + pl.off_cur_val);
+    P.nxt_id = (int *)(base + pl.off_nxt_id);
+    P.sup_id = (int *)(base + pl.off_sup_id);
+    P.cand_val = (double *)(base + pl.off_cand);
+    P.capF = pl.capF; P.capS = pl.capS;
+    P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1;
+    rc = pl.block == 256 ? launch_push<256>(P, pl, stream)
+         : pl.block == 512 ? launch_push<512>(P, pl, stream)
+                           : launch_push<1024>(P, pl, stream);
+    if (rc != GP_OK) return rc;
+    g->last.sources = S; g->last.ctas = pl.ctas; g->last.scratch_bytes = (int64_t)g->scratch_bytes;
+    g->last.scratch_mode = pl.mode; g->last.kernel_launches = 1;
+    return GP_OK;
+}
+
+// Reads the control block back (synchronises `stream`) and turns device-side flags into errors.
+int collect_stats(gp_graph *g, cudaStream_t stream) {
+    unsigned long long h[8];
+    GP_CUDA_TRY(cudaMemcpyAsync(h, g->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, stream));
+    GP_CUDA_TRY(cudaStreamSynchronize(stream));
+    g->last.edges_pushed = (int64_t)h[1];
+    g->last.frontier_total = (int64_t)h[2];
+    g->last.support_total = (int64_t)h[3];
+    if (h[4] & kErrBadSource) { gp_set_error("node_idx contains an id outside [0, %lld)", g->n); return GP_ERR_INVALID; }
+    if (h[4] & kErrOverflow) { gp_set_error("frontier/support list outgrew its bound (rmax too small for the budget?)"); return GP_ERR_OVERFLOW; }
+    return GP_OK;
+}
+
+int graph_finish_create(gp_graph *g) {
+    cudaDeviceProp prop;
+    GP_CUDA_TRY(cudaGetDeviceProperties(&prop, g->device));
+    g->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : GP_NUM_SMS_FALLBACK;
+    g->smem_optin = prop.sharedMemPerBlockOptin;
+    GP_CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    GP_CUDA_TRY(cudaMalloc(&g->d_coef, sizeof(double) * kMaxLevels));
+    GP_CUDA_TRY(cudaMalloc(&g->d_ctrl, sizeof(unsigned long long) * 8));
+    // validate the CSR once, on the device (the reference validates nothing)
+    int *d_flag = (int *)(g->d_ctrl);
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 8, g->stream));
+    validate_csr_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(g->d_indptr, g->n, g->d_indices, g->nnz, d_flag);
+    GP_CUDA_TRY(cudaGetLastError());
+    int flag = 0;
+    GP_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
+    GP_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    GP_REQUIRE(flag == 0, "malformed CSR: indptr must start at 0, be non-decreasing and end at nnz; indices must lie in [0, n)");
+    return GP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gp_graph_create(const int32_t *indptr, int64_t n_nodes, const int32_t *indices, int64_t nnz, int32_t seed,
+                    int device, gp_graph **out) {
+    (void)seed;  // stored and never read by the reference either (graph.h:30,40)
+    GP_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    GP_REQUIRE(indptr != nullptr && (indices != nullptr || nnz == 0), "null CSR array");
+    GP_REQUIRE(n_nodes >= 1 && n_nodes < (1ll << 31) - 1, "n_nodes out of range: %lld", (long long)n_nodes);
+    GP_REQUIRE(nnz >= 0 && nnz < (1ll << 31), "nnz out of range for int32 CSR: %lld", (long long)nnz);
+    GP_REQUIRE(gp_device_count() > 0, "no CUDA device: this library has no CPU fallback");
+    DeviceGuard guard(device);
+    GP_REQUIRE(guard.ok, "cannot select CUDA device %d", device);
+    gp_graph *g = new (std::nothrow) gp_graph();
+    if (!g) { gp_set_error("out of host memory"); return GP_ERR_NOMEM; }
+    g->device = device; g->n = n_nodes; g->nnz = nnz; g->owns_csr = true;
+    auto fail = [&](int rc) { gp_graph_destroy(g); return rc; };
+    cudaError_t e = cudaMalloc(&g->d_indptr, sizeof(int) * (size_t)(n_nodes + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_indices, sizeof(int) * (size_t)std::max<int64_t>(nnz, 1));
+    if (e == cudaSuccess) e = cudaMemcpy(g->d_indptr, indptr, sizeof(int) * (size_t)(n_nodes + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nnz) e = cudaMemcpy(g->d_indices, indices, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { gp_set_error("CSR upload failed: %s", cudaGetErrorString(e)); return fail(e == cudaErrorMemoryAllocation ? GP_ERR_NOMEM : GP_ERR_CUDA); }
+    int rc = graph_finish_create(g);
+    if (rc != GP_OK) return fail(rc);
+    *out = g;
+    return GP_OK;
+}
+
+int gp_graph_create_device(const int32_t *d_indptr, int64_t n_nodes, const int32_t *d_indices, int64_t nnz,
+                           int device, gp_graph **out) {
+    GP_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    GP_REQUIRE(d_indptr != nullptr && (d_indices != nullptr || nnz == 0), "null CSR array");
+    GP_REQUIRE(n_nodes >= 1 && n_nodes < (1ll << 31) - 1, "n_nodes out of range: %lld", (long long)n_nodes);
+    GP_REQUIRE(nnz >= 0 && nnz < (1ll << 31), "nnz out of range for int32 CSR: %lld", (long long)nnz);
+    GP_REQUIRE(gp_device_count() > 0, "no CUDA device: this library has no CPU fallback");
+    DeviceGuard guard(device);
+    GP_REQUIRE(guard.ok, "cannot select CUDA device %d", device);
+    gp_graph *g = new (std::nothrow) gp_graph();
+    if (!g) { gp_set_error("out of host memory"); return GP_ERR_NOMEM; }
+    g->device = device; g->n = n_nodes; g->nnz = nnz; g->owns_csr = false;
+    g->d_indptr = const_cast<int *>(d_indptr);
+    g->d_indices = const_cast<int *>(d_indices);
+    int rc = graph_finish_create(g);
+    if (rc != GP_OK) { gp_graph_destroy(g); return rc; }
+    *out = g;
+    return GP_OK;
+}
+
+void gp_graph_destroy(gp_graph *g) {
+    if (!g) return;
+    DeviceGuard guard(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    if (g->owns_csr) { cudaFree(g->d_indptr); cudaFree(g->d_indices); }
+    cudaFree(g->scratch); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+int64_t gp_graph_num_nodes(const gp_graph *g) { return g ? g->n : 0; }
+int64_t gp_graph_num_edges(const gp_graph *g) { return g ? g->nnz : 0; }
+
+int gp_graph_configure(gp_graph *g, const gp_push_config *cfg) {
+    GP_REQUIRE(g && cfg, "null argument");
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->cfg = *cfg;
+    return GP_OK;
+}
+
+int gp_gfpush_device(gp_graph *g, const int32_t *d_node_idx, int64_t S, const double *coef, int32_t L, double rmax,
+                     int32_t K, int32_t *d_row_idx, int32_t *d_col_idx, double *d_value, float *d_value32,
+                     void *stream) {
+    GP_REQUIRE(g != nullptr, "graph handle is null");
+    std::lock_guard<std::mutex> lk(g->mu);
+    DeviceGuard guard(g->device);
+    GP_REQUIRE(guard.ok, "cannot select CUDA device %d", g->device);
+    return push_device_locked(g, d_node_idx, S, coef, L, rmax, K, d_row_idx, d_col_idx, d_value, d_value32,
+                              (cudaStream_t)stream);
+}
+
+int gp_gfpush(gp_graph *g, const int32_t *node_idx, int64_t S, const double *coef, int32_t L, double rmax, int32_t K,
+              int32_t *row_idx, int32_t *col_idx, double *value) {
+    GP_REQUIRE(g != nullptr, "graph handle is null");
+    GP_REQUIRE(S >= 0, "negative source count");
+    if (S == 0) return GP_OK;
+    GP_REQUIRE(node_idx && row_idx && col_idx && value, "null host buffer");
+    GP_REQUIRE(K >= 1 && K <= kMaxK, "top_k must be in 1..%d (got %d)", kMaxK, K);
+    std::lock_guard<std::mutex> lk(g->mu);
+    DeviceGuard guard(g->device);
+    GP_REQUIRE(guard.ok, "cannot select CUDA device %d", g->device);
+    const size_t slots = (size_t)S * (size_t)K;
+    if (g->d_node_cap < (size_t)S) {
+        cudaFree(g->d_node); g->d_node = nullptr; g->d_node_cap = 0;
+        GP_CUDA_TRY(cudaMalloc(&g->d_node, sizeof(int) * (size_t)S));
+        g->d_node_cap = (size_t)S;
+    }
+    const size_t out_bytes = slots * 16;
+    if (g->d_out_cap < out_bytes) {
+        cudaFree(g->d_out); g->d_out = nullptr; g->d_out_cap = 0;
+        GP_CUDA_TRY(cudaMalloc(&g->d_out, out_bytes));
+        g->d_out_cap = out_bytes;
+    }
+    double *d_val = (double *)g->d_out;
+    int *d_row = (int *)((char *)g->d_out + slots * 8);
+    int *d_col = d_row + slots;
+    GP_CUDA_TRY(cudaMemcpyAsync(g->d_node, node_idx, sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, g->stream));
+    int rc = push_device_locked(g, g->d_node, S, coef, L, rmax, K, d_row, d_col, d_val, nullptr, g->stream);
+    if (rc != GP_OK) return rc;
+    GP_CUDA_TRY(cudaMemcpyAsync(value, d_val, slots * 8, cudaMemcpyDeviceToHost, g->stream));
+    GP_CUDA_TRY(cudaMemcpyAsync(row_idx, d_row, slots * 4, cudaMemcpyDeviceToHost, g->stream));
+    GP_CUDA_TRY(cudaMemcpyAsync(col_idx, d_col, slots * 4, cudaMemcpyDeviceToHost, g->stream));
+    return collect_stats(g, g->stream);
+}
+
+int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out) {
+    GP_REQUIRE(g && out, "null argument");
+    std::lock_guard<std::mutex> lk(g->mu);
+    DeviceGuard guard(g->device);
+    if (g->last.sources > 0 && g->last.kernel_launches > 0) {
+        // the device-pointer entry point is asynchronous: wait for whatever stream it ran on
+        GP_CUDA_TRY(cudaDeviceSynchronize());
+        int rc = collect_stats(g, g->stream);
+        if (rc != GP_OK) { *out = g->last; return rc; }
+    }
+    *out = g->last;
+    return GP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,199 @@
+"""GPU parity tests, part 1: GFPush + top-k through the C ABI (Graph.gfpush_omp -> gp_gfpush)
+against the reference's golden vectors and the oracle.  Run with -m gpu on the B200 box."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gfpush as og
+from tests.helpers import GOLDEN, check_topk_rows, load_graph
+
+pytestmark = pytest.mark.gpu
+
+DATASETS = ["cora", "citeseer", "pubmed"]
+MODES = ["ppr", "avg", "single"]
+SMEM, HBM = 1, 2
+
+
+def _graph(indptr, indices, **cfg):
+    from grandplus_b200.precompute import propagation
+    g = propagation.Graph(np.array(indptr, dtype=np.int32), np.array(indices, dtype=np.int32), 0)
+    if cfg:
+        g.configure(**cfg)
+    return g
+
+
+def _run(g, node_idx, coef, rmax, K):
+    S = len(node_idx)
+    row = np.zeros(S * K, dtype=np.int32)
+    col = np.zeros(S * K, dtype=np.int32)
+    val = np.zeros(S * K, dtype=np.float64)
+    g.gfpush_omp(node_idx, row, col, val, coef, rmax, K)  # exactly model.py:268
+    return row, col, val
+
+
+@pytest.mark.parametrize("name", DATASETS)
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("scratch", [SMEM, HBM])
+def test_gfpush_matches_reference_golden(name, mode, scratch):
+    indptr, indices = load_graph(name)
+    z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
+    K, rmax = int(z["K"]), float(z["rmax"])
+    g = _graph(indptr, indices, scratch_mode=scratch)
+    row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)  # int64 like model.py:247
+    assert g.last_stats()["scratch_mode"] == scratch
+    worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
+    assert worst < 1e-11, worst
+    # against the reference's own rows: identical sets wherever the reference row has no tie at the cut
+    same = 0
+    for (gc, gv), (rc, rv) in zip(og.rows_as_sets(col, val, K), og.rows_as_sets(z["col_idx"], z["value"], K)):
+        assert len(gc) == len(rc)
+        if np.array_equal(gc, rc):
+            same += 1
+            np.testing.assert_allclose(gv, rv, rtol=1e-11, atol=0)   # north_star asks 1e-5
+    assert same >= (0.5 if mode == "ppr" else 0.2) * len(z["node_idx"])
+
+
+@pytest.mark.parametrize("name", ["path8", "star33", "isolated", "dangling"])
+@pytest.mark.parametrize("scratch", [SMEM, HBM])
+def test_gfpush_tiny_graphs(name, scratch):
+    z = np.load(os.path.join(GOLDEN, f"tiny_{name}.npz"))
+    g = _graph(z["indptr"], z["indices"], scratch_mode=scratch)
+    for tag in sorted({k.split("/")[0] for k in z.files if "/" in k}):
+        K, rmax, coef = int(z[f"{tag}/K"]), float(z[f"{tag}/rmax"]), z[f"{tag}/coef"]
+        row, col, val = _run(g, z["node_idx"], coef, rmax, K)
+        check_topk_rows(z["indptr"], z["indices"], z["node_idx"], coef, rmax, K, col, val, row=row)
+        # same number of filled slots as the reference, row by row
+        ref_filled = (z[f"{tag}/value"].reshape(-1, K) > 0).sum(1)
+        np.testing.assert_array_equal((val.reshape(-1, K) > 0).sum(1), ref_filled)
+
+
+@pytest.mark.parametrize("block", [256, 512, 1024])
+@pytest.mark.parametrize("scratch", [SMEM, HBM])
+def test_gfpush_all_sources_cora_block_sizes(block, scratch):
+    """Every node of Cora as a source (S=N), ppr at scripts/run_cora.sh:7 parameters."""
+    indptr, indices = load_graph("cora")
+    n = indptr.shape[0] - 1
+    coef = og.coef_for("ppr", 20, 0.2)
+    g = _graph(indptr, indices, scratch_mode=scratch, block_threads=block)
+    src = np.arange(n, dtype=np.int32)
+    row, col, val = _run(g, src, coef, 1e-7, 32)
+    st = g.last_stats()
+    assert st["sources"] == n
+    _, _, _, ost = og.gfpush(indptr, indices, src, coef, 1e-7, 32)
+    # work counters are integers of the algorithm: exact unless a threshold comparison flipped
+    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * ost.edges_pushed
+    assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
+    check_topk_rows(indptr, indices, src, coef, 1e-7, 32, col, val, row=row, max_rows=200)
+
+
+def test_gfpush_idempotent_and_order_independent():
+    indptr, indices = load_graph("pubmed")
+    coef = og.coef_for("ppr", 6, 0.5)
+    rng = np.random.default_rng(5)
+    src = rng.choice(indptr.shape[0] - 1, 512, replace=False).astype(np.int32)
+    g = _graph(indptr, indices)
+    a = og.rows_as_sets(*_run(g, src, coef, 1e-5, 16)[1:], 16)
+    b = og.rows_as_sets(*_run(g, src, coef, 1e-5, 16)[1:], 16)
+    perm = rng.permutation(len(src))
+    c = og.rows_as_sets(*_run(g, src[perm], coef, 1e-5, 16)[1:], 16)
+    for i in range(len(src)):
+        for other in (b[i], c[int(np.nonzero(perm == i)[0][0])]):
+            if np.array_equal(a[i][0], other[0]):
+                np.testing.assert_allclose(a[i][1], other[1], rtol=1e-12)
+            else:  # only a tie at the cut may differ
+                assert len(a[i][0]) == len(other[0])
+                assert abs(a[i][1].min() - other[1].min()) <= 1e-12 * a[i][1].min()
+
+
+def test_gfpush_mass_conservation_full_rows():
+    """rmax = 0 and K >= support: nothing is dropped, every row sums to 1 (coef sums to 1)."""
+    z = np.load(os.path.join(GOLDEN, "tiny_star33.npz"))
+    g = _graph(z["indptr"], z["indices"])
+    coef = og.coef_for("ppr", 8, 0.3)
+    _, _, val = _run(g, z["node_idx"], coef, 0.0, 64)
+    np.testing.assert_allclose(val.reshape(-1, 64).sum(1), 1.0, rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("scratch", [HBM])
+def test_gfpush_powerlaw_synthetic(scratch):
+    """A Chung-Lu graph with hubs (max degree in the thousands): CTA-wide hub expansion, HBM slabs."""
+    from grandplus_b200 import synth
+    indptr, indices = synth.powerlaw_csr(50_000, 600_000, seed=3)
+    indptr, indices = indptr.numpy(), indices.numpy()
+    deg = np.diff(indptr)
+    src = np.concatenate([[int(np.argmax(deg))], synth.sources(50_000, 255, seed=2).numpy()]).astype(np.int32)
+    for mode, order, alpha, rmax, K in [("ppr", 6, 0.05, 1e-5, 32), ("avg", 4, 0.2, 1e-6, 64), ("single", 2, 0.2, 1e-7, 64)]:
+        coef = og.coef_for(mode, order, alpha)
+        g = _graph(indptr, indices, scratch_mode=scratch)
+        row, col, val = _run(g, src, coef, rmax, K)
+        worst = check_topk_rows(indptr, indices, src, coef, rmax, K, col, val, row=row, max_rows=64)
+        assert worst < 1e-11
+        _, _, _, ost = og.gfpush(indptr, indices, src, coef, rmax, K)
+        st = g.last_stats()
+        assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * max(ost.edges_pushed, 1)
+        assert st["support_total"] == ost.support_total or abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
+
+
+def test_gfpush_device_resident_outputs_match_host_path():
+    import torch
+    indptr, indices = load_graph("citeseer")
+    coef = og.coef_for("ppr", 10, 0.4)
+    src = np.arange(0, 3327, 13, dtype=np.int32)
+    g = _graph(indptr, indices)
+    row, col, val = _run(g, src, coef, 1e-7, 32)
+    drow, dcol, dval, dval32 = g.gfpush_device(torch.from_numpy(src).cuda(), coef, 1e-7, 32)
+    torch.cuda.synchronize()
+    a = og.rows_as_sets(col, val, 32)
+    b = og.rows_as_sets(dcol.cpu().numpy().ravel(), dval.cpu().numpy().ravel(), 32)
+    for (ac, av), (bc, bv) in zip(a, b):
+        if np.array_equal(ac, bc):
+            np.testing.assert_allclose(av, bv, rtol=1e-12)
+    np.testing.assert_array_equal(dval32.cpu().numpy(), dval.cpu().numpy().astype(np.float32))
+    assert np.all(drow.cpu().numpy()[dval.cpu().numpy() > 0] == np.repeat(src, 32).reshape(-1, 32)[dval.cpu().numpy() > 0])
+
+
+def test_gfpush_rejects_bad_arguments():
+    from grandplus_b200._lib import GPError
+    indptr, indices = load_graph("cora")
+    g = _graph(indptr, indices)
+    coef = og.coef_for("ppr", 4, 0.2)
+    S, K = 4, 8
+    row = np.zeros(S * K, np.int32); col = np.zeros(S * K, np.int32); val = np.zeros(S * K, np.float64)
+    with pytest.raises(ValueError):
+        g.gfpush_omp(np.arange(S), row, col, val.astype(np.float32), coef, 1e-5, K)   # wrong dtype
+    with pytest.raises(ValueError):
+        g.gfpush_omp(np.arange(S), row[:-1], col, val, coef, 1e-5, K)                   # too short
+    with pytest.raises(ValueError):
+        g.gfpush_omp(np.array([0, 1, 99999, 2]), row, col, val, coef, 1e-5, K)          # id out of range
+    with pytest.raises(GPError):
+        g.gfpush_omp(np.arange(S), np.zeros(S * 4096, np.int32), np.zeros(S * 4096, np.int32),
+                     np.zeros(S * 4096, np.float64), coef, 1e-5, 4096)                  # K too large
+    bad_ptr = indptr.copy(); bad_ptr[5] = bad_ptr[4] - 1
+    with pytest.raises(GPError):
+        _graph(bad_ptr, indices)
+    # empty source list is a no-op, like the reference's empty omp loop
+    g.gfpush_omp(np.zeros(0, np.int64), row[:0], col[:0], val[:0], coef, 1e-5, K)
+
+
+@pytest.mark.skipif(not og.reference_available(), reason="oracle/_ref not shipped to this box")
+def test_gfpush_vs_live_reference_all_pubmed_sources():
+    """Full Pubmed (BASELINE config 2), every node a source, against the reference module itself."""
+    indptr, indices = load_graph("pubmed")
+    n = indptr.shape[0] - 1
+    coef = og.coef_for("ppr", 6, 0.5)
+    src = np.arange(n, dtype=np.int32)
+    g = _graph(indptr, indices)
+    row, col, val = _run(g, src, coef, 1e-5, 16)
+    rrow, rcol, rval = og.reference_gfpush(indptr, indices, src, coef, 1e-5, 16)
+    mine, ref = og.rows_as_sets(col, val, 16), og.rows_as_sets(rcol, rval, 16)
+    same, worst = 0, 0.0
+    for (gc, gv), (rc, rv) in zip(mine, ref):
+        assert len(gc) == len(rc)
+        if np.array_equal(gc, rc):
+            same += 1
+            worst = max(worst, float(np.max(np.abs(gv - rv) / rv)))
+        else:
+            assert abs(gv.min() - rv.min()) <= 1e-9 * rv.min()   # differs only by a tie at the cut
+    assert worst < 1e-11
+    assert same > 0.8 * n
