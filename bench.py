@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- GRAND+ propagation hot path on B200: GFPush source rows/s and Pi.X aggregation GB/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload reddit] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of S sources of the workload graph:
+  (1) GFPush + top-k of the S sources (gp_gfpush_device; Pi rows stay in HBM), then
+  (2) the DropNode-masked Pi.X aggregation of those S rows, `sample`=2 augmentations in one launch
+      (gp_aggregate_fwd, slot layout, p=0.5 -- /root/reference/model.py:321-322).
+`value` is whole-job source rows/s with inputs resident in HBM; `e2e` is the same metric through the
+reference-facing calls with HOST (pinned) buffers: Graph.gfpush_omp(host arrays) [H2D node ids, D2H
+row/col/value], upload of the batch's (neighbor, score) arrays as /root/reference/model.py:314-316
+does, the fused aggregation, and a D2H read of the result checksum.  Multi-GPU: sources are sharded
+over ranks on a replicated CSR with no data-path collective (weak scaling: S per rank is fixed).
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref = its propagation.cpp
+compiled unmodified; falls back to the oracle port) on the host cores, on a bounded source sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "gfpush_source_rows_per_s"
+UNIT = "rows/s"
+
+# BASELINE.json configs.  Parameters: scripts/run_<dataset>.sh line 7 (ppr); K for reddit per BASELINE.
+WORKLOADS = {
+    "cora": dict(config=0, real="cora", F=1433, mode="ppr", order=20, alpha=0.2, rmax=1e-7, K=32, S=2708),
+    "pubmed": dict(config=1, real="pubmed", F=500, mode="ppr", order=6, alpha=0.5, rmax=1e-5, K=16, S=19717),
+    "reddit": dict(config=2, n=232_965, draws=11_606_919, F=602, mode="ppr", order=6, alpha=0.05, rmax=1e-5, K=32,
+                   S=16384),
+    "amazon2m": dict(config=3, n=2_449_029, draws=61_859_140, F=100, mode="ppr", order=6, alpha=0.2, rmax=1e-6,
+                     K=64, S=4096),
+    "small": dict(config=-1, n=50_000, draws=600_000, F=64, mode="ppr", order=6, alpha=0.05, rmax=1e-5, K=32, S=2048),
+}
+DROPNODE_P = 0.5   # run_model.py:56 default
+N_AUG = 2          # run_model.py --sample default (model.py:321)
+
+
+def coef_for(mode, order, alpha):
+    """model.py:255-267."""
+    if mode == "avg":
+        c = np.ones(order + 1)
+    elif mode == "ppr":
+        c = alpha * (1 - alpha) ** np.arange(order + 1)
+    else:
+        c = np.zeros(order + 1); c[-1] = 1.0
+    return (c / c.sum()).astype(np.float64)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(workload, kernel):
+    """dram bytes per launch from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(p))[workload][kernel]
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.samples.append(line.strip())
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def build_workload(name, device):
+    """(indptr, indices) int32 torch tensors on `device`, features tensor [n,F] on `device`."""
+    import torch
+    from grandplus_b200 import synth
+    w = WORKLOADS[name]
+    if "real" in w:
+        z = np.load(os.path.join(ROOT, "tests", "golden", f"graph_{w['real']}.npz"))
+        indptr = torch.from_numpy(z["indptr"]).to(device)
+        indices = torch.from_numpy(z["indices"]).to(device)
+    else:
+        indptr, indices = synth.powerlaw_csr(w["n"], w["draws"], seed=0, device=device)
+    n = int(indptr.numel() - 1)
+    return indptr, indices, n
+
+
+def source_batches(n, S, count, rank, world, device):
+    """`count` batches of S distinct sources for this rank: consecutive slices of one seeded
+    permutation of the nodes (wrapping), disjoint across ranks within a step."""
+    from grandplus_b200 import synth
+    perm = synth.sources(n, n, seed=1, device=device)
+    out = []
+    for i in range(count):
+        start = ((i * world + rank) * S) % n
+        idx = (start + np.arange(S)) % n
+        import torch
+        out.append(perm[torch.as_tensor(idx, device=perm.device)].contiguous())
+    return out
+
+
+def algorithmic_bytes_gfpush(stats, S_total, K):
+    """E_push*(4+8) + F_tot*(8+8) + K*16 per source."""
+    return stats["edges_pushed"] * 12 + stats["frontier_total"] * 16 + S_total * K * 16
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from grandplus_b200 import dist as gd
+    from grandplus_b200 import model as gm
+    from grandplus_b200 import synth
+    from grandplus_b200.precompute import propagation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = WORKLOADS[args.workload]
+    S = args.sources or w["S"]
+    K = w["K"]
+    coef = coef_for(w["mode"], w["order"], w["alpha"])
+
+    t_setup = time.time()
+    indptr, indices, n = build_workload(args.workload, dev)
+    S = min(S, n)
+    graph = propagation.Graph.from_device_csr(indptr, indices)
+    if args.scratch or args.block or args.ctas_per_sm:
+        graph.configure(scratch_mode=args.scratch, block_threads=args.block, ctas_per_sm=args.ctas_per_sm)
+    X = synth.features(n, w["F"], seed=1, device=dev)
+    feats = gm.DeviceFeatures(X)
+    del X
+    total = args.warmup + args.steps
+    batches = source_batches(n, S, total, rank, world, dev)
+    torch.cuda.synchronize()
+    t_setup = time.time() - t_setup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ------------------------------------------------------------------ device-resident timing
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    checks = []
+    for i in range(total):
+        if i == args.warmup:
+            torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
+            graph.cumulative_stats(reset=True)
+            sampler.start()
+            t0 = time.perf_counter()
+        timed = i >= args.warmup
+        if timed:
+            ev[i - args.warmup][0].record()
+        _row, col, _val, val32 = graph.gfpush_device(batches[i], coef, w["rmax"], K, want_fp32=True)
+        if timed:
+            ev[i - args.warmup][1].record()
+        out = gm.aggregate_slots(feats, col, val32, None, DROPNODE_P, True, n_aug=N_AUG, seed=1234, offset=i)
+        if timed:
+            ev[i - args.warmup][2].record()
+        checks.append(out[0, 0, 0])
+    torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t_push = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
+    t_agg = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
+    t_dev = ev[0][0].elapsed_time(ev[-1][2]) / 1e3   # CUDA events on the launching stream, first to last timed launch
+    stats = graph.cumulative_stats(reset=True)
+    step_time = gd.max_over_ranks(t_dev, device=dev)  # max over ranks
+    wall = gd.max_over_ranks(wall, device=dev)
+    rows_total = S * args.steps * world
+    value = rows_total / step_time
+
+    # algorithmic bytes of the aggregation (untimed post-pass: the masks are counter-based, so the
+    # kept-entry count of every timed step can be regenerated exactly)
+    agg_bytes = 0
+    slots = S * K
+    for i in range(args.warmup, total):
+        _row, col, _val, val32 = graph.gfpush_device(batches[i], coef, w["rmax"], K, want_fp32=True)
+        mask = gm.dropnode_mask(slots, N_AUG, DROPNODE_P, 1234, i, dev)
+        kept_any = ((mask.sum(0) > 0) & (val32.reshape(-1) > 0)).sum().item()
+        agg_bytes += kept_any * w["F"] * 4 + slots * 8 + (S + 1) * 4 + N_AUG * S * w["F"] * 4
+    graph.cumulative_stats(reset=True)
+    push_bytes = algorithmic_bytes_gfpush(stats, S * args.steps, K)
+    peak, peak_src = load_peaks()
+    roof_push = {"kernel": "gfpush_kernel", "bound": "hbm", "achieved": push_bytes / t_push / 1e9, "peak": peak,
+                 "unit": "GB/s", "frac": push_bytes / t_push / 1e9 / peak,
+                 "traffic": load_traffic(args.workload, "gfpush_kernel"), "peak_source": peak_src,
+                 "ms_per_launch": t_push / args.steps * 1e3, "share_of_step": t_push / t_dev,
+                 "edges_per_s": stats["edges_pushed"] / t_push, "edges_per_source": stats["edges_pushed"] / (S * args.steps),
+                 "algorithmic_bytes_per_launch": push_bytes / args.steps}
+    roof_agg = {"kernel": "aggregate_fwd_kernel", "bound": "hbm", "achieved": agg_bytes / t_agg / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": agg_bytes / t_agg / 1e9 / peak,
+                "traffic": load_traffic(args.workload, "aggregate_fwd_kernel"), "peak_source": peak_src,
+                "ms_per_launch": t_agg / args.steps * 1e3, "share_of_step": t_agg / t_dev,
+                "algorithmic_bytes_per_launch": agg_bytes / args.steps, "rows_per_s": S * args.steps / t_agg}
+    dominant = roof_push if t_push >= t_agg else roof_agg
+
+    # ------------------------------------------------------------------ end-to-end, host buffers
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)  # noqa: E731
+    h_node = pin((S,), torch.int32)
+    h_row, h_col, h_val = pin((S * K,), torch.int32), pin((S * K,), torch.int32), pin((S * K,), torch.float64)
+    host_batches = [b.cpu() for b in batches]
+    torch.cuda.synchronize(); barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    for i in range(2 + e2e_steps):
+        if i == 2:
+            torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        h_node.copy_(host_batches[(args.warmup + i) % total])
+        graph.gfpush_omp(h_node.numpy(), h_row.numpy(), h_col.numpy(), h_val.numpy(), coef, w["rmax"], K)
+        d_col = h_col.to(dev, non_blocking=True).reshape(S, K)              # model.py:314-316: the batch's
+        d_val = h_val.to(dev, non_blocking=True).reshape(S, K).float()      # neighbour ids and scores go H2D
+        out = gm.aggregate_slots(feats, d_col, d_val, None, DROPNODE_P, True, n_aug=N_AUG, seed=1234, offset=i)
+        chk = float(out.sum().item())                                       # D2H read of the step's result
+    torch.cuda.synchronize(); barrier()
+    e2e_time = gd.max_over_ranks(time.perf_counter() - t0, device=dev)
+    e2e = {"value": S * e2e_steps * world / e2e_time, "unit": UNIT, "h2d_bytes_per_step": S * 4 + S * K * 12,
+           "d2h_bytes_per_step": S * K * 16 + 4, "steps": e2e_steps, "ms_per_step": e2e_time / e2e_steps * 1e3,
+           "api": "Graph.gfpush_omp(host arrays) + aggregate_slots(H2D col/score) + checksum D2H", "checksum": chk}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_time / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (GFPush residues) / f32 (aggregation)", "data": "synthetic" if "real" not in w else
+        f"real {w['real']} graph (Planetoid, tests/golden) + synthetic N(0,1) features",
+        "config": {"workload": f"BASELINE configs[{w['config']}] {args.workload}", "nodes": n,
+                   "csr_nnz": int(indices.numel()), "features": w["F"], "prop_mode": w["mode"], "order": w["order"],
+                   "alpha": w["alpha"], "rmax": w["rmax"], "top_k": K, "sources_per_step_per_gpu": S,
+                   "dropnode_rate": DROPNODE_P, "augmentations": N_AUG, "parallelism": f"source-sharded x{world}, CSR+X replicated",
+                   "l2": "inputs larger than L2 (X %.0f MB, CSR %.0f MB, per-CTA tables %.0f MB); new sources every step"
+                         % (feats.data.numel() * 4 / 1e6, (indices.numel() + indptr.numel()) * 4 / 1e6, stats["scratch_bytes"] / 1e6),
+                   "scratch_mode": {1: "smem", 2: "hbm"}.get(stats["scratch_mode"]), "persistent_ctas": stats["ctas"]},
+        "roofline": dominant, "roofline_gfpush": roof_push, "roofline_aggregate": roof_agg,
+        "aggregation_gb_per_s": roof_agg["achieved"],
+        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+        "setup_s": t_setup, "impl": "ours", "wall_ms_per_step": wall / args.steps * 1e3,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.workload, indptr.cpu().numpy(), indices.cpu().numpy(), n,
+                                            budget_s=args.cpu_budget)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def _cpu_step(name, indptr, indices, n, src, X, use_ref):
+    """One pass of the reference CPU path over `src`: GFPush (reference .so, 40 OpenMP threads as
+    graph.h:41 hard-codes; or the oracle port) + the host gather / scatter aggregation of those rows
+    for N_AUG augmentations (model.py:80-87,314 restated with index_add_)."""
+    import torch
+    from oracle import gfpush as og
+    w = WORKLOADS[name]
+    coef = coef_for(w["mode"], w["order"], w["alpha"])
+    K = w["K"]
+    t0 = time.perf_counter()
+    if use_ref:
+        row, col, val = og.reference_gfpush(indptr, indices, src, coef, w["rmax"], K)
+    else:
+        row, col, val, _ = og.gfpush(indptr, indices, src, coef, w["rmax"], K, nthreads=0)
+    t1 = time.perf_counter()
+    S = len(src)
+    idx = torch.arange(S).repeat_interleave(K)
+    colt = torch.from_numpy(col.astype(np.int64))
+    sc = torch.from_numpy(val.astype(np.float32))
+    live = sc > 0
+    idx, colt, sc = idx[live], colt[live], sc[live]
+    for _ in range(N_AUG):
+        m = torch.nn.functional.dropout(sc, DROPNODE_P, True)
+        f = X[colt]                                              # model.py:314 host gather
+        num = torch.zeros(S, X.shape[1]).index_add_(0, idx, f * m[:, None])
+        den = torch.zeros(S, 1).index_add_(0, idx, m[:, None])
+        _ = num / (den + 1e-12)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
+def cpu_baseline(name, indptr, indices, n, budget_s=15.0):
+    import torch
+    from oracle import gfpush as og
+    w = WORKLOADS[name]
+    use_ref = og.reference_available()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(1)
+    X = torch.randn(n, w["F"])
+    probe = rng.choice(n, size=min(n, 16), replace=False).astype(np.int32)
+    tp, ta = _cpu_step(name, indptr, indices, n, probe, X, use_ref)
+    per = max((tp + ta) / len(probe), 1e-6)
+    S = int(max(16, min(n, budget_s / per)))
+    src = rng.choice(n, size=S, replace=False).astype(np.int32)
+    tp, ta = _cpu_step(name, indptr, indices, n, src, X, use_ref)
+    return {"value": S / (tp + ta), "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": f"{S} sources of the same graph (GFPush {tp:.2f} s + aggregation {ta:.2f} s)",
+            "gfpush_rows_per_s": S / tp, "aggregate_rows_per_s": S / ta,
+            "threads": "reference hard-codes 40 OpenMP threads (graph.h:41); torch aggregation uses all cores"
+            if use_ref else f"{cores} OpenMP threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from grandplus_b200 import synth
+    from oracle import gfpush as og
+    w = WORKLOADS[args.workload]
+    if "real" in w:
+        z = np.load(os.path.join(ROOT, "tests", "golden", f"graph_{w['real']}.npz"))
+        indptr, indices = z["indptr"], z["indices"]
+    else:
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        ip, ix = synth.powerlaw_csr(w["n"], w["draws"], seed=0, device=dev)
+        indptr, indices = ip.cpu().numpy(), ix.cpu().numpy()
+    n = len(indptr) - 1
+    use_ref = og.reference_available()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    X = torch.randn(n, w["F"])
+    rng = np.random.default_rng(1)
+    probe = rng.choice(n, size=min(n, 16), replace=False).astype(np.int32)
+    tp, ta = _cpu_step(args.workload, indptr, indices, n, probe, X, use_ref)
+    per = max((tp + ta) / len(probe), 1e-6)
+    total = args.steps + args.warmup
+    S = int(max(16, min(n, args.ref_budget / total / per)))
+    times = []
+    for i in range(total):
+        src = rng.choice(n, size=S, replace=False).astype(np.int32)
+        tp, ta = _cpu_step(args.workload, indptr, indices, n, src, X, use_ref)
+        if i >= args.warmup:
+            times.append((tp, ta))
+    t = sum(a + b for a, b in times)
+    value = S * args.steps / t
+    kind = "reference" if use_ref else "port"
+    sample = f"{S} sources per step of the same graph, {args.steps} steps"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (GFPush residues) / f32 (aggregation)",
+            "data": "synthetic" if "real" not in w else f"real {w['real']} graph + synthetic features",
+            "config": {"workload": f"BASELINE configs[{w['config']}] {args.workload}", "nodes": n, "csr_nnz": int(len(indices)),
+                       "features": w["F"], "prop_mode": w["mode"], "order": w["order"], "alpha": w["alpha"],
+                       "rmax": w["rmax"], "top_k": w["K"], "dropnode_rate": DROPNODE_P, "augmentations": N_AUG},
+            "impl": "reference",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                             "gfpush_rows_per_s": S * args.steps / sum(a for a, _ in times),
+                             "aggregate_rows_per_s": S * args.steps / sum(b for _, b in times)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS))
+    ap.add_argument("--sources", type=int, default=0, help="sources per step per GPU (default: workload's)")
+    ap.add_argument("--scratch", type=int, default=0, help="0 auto, 1 smem, 2 hbm")
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of CPU work for --impl reference")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

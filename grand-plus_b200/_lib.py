@@ -81,6 +81,7 @@ SIGNATURES = {
     "gp_gfpush_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_double,
                                         ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "gp_gfpush_last_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(PushStats)]),
+    "gp_gfpush_cumulative_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(PushStats), ctypes.c_int]),
     "gp_aggregate_fwd": (ctypes.c_int, [ctypes.POINTER(AggregateArgs), c_vp]),
     "gp_aggregate_bwd": (ctypes.c_int, [ctypes.POINTER(AggregateBwdArgs), c_vp]),
     "gp_segments_from_sorted_index": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp]),
@@ -97,11 +98,16 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
-            raise ImportError(f"{LIB_PATH} is missing; run `python __graft_entry__.py build`")
+    if build_if_missing:
+        # content-stamped: a no-op when the objects match the sources, a rebuild when they are stale
         from . import build as _build
-        _build.build()
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing; run `python __graft_entry__.py build`")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

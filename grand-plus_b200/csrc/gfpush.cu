@@ -63,6 +63,7 @@ struct PushParams {
     long long capF, capS;
     unsigned long long *queue;  // [1] next source
     unsigned long long *stats;  // [0] edges [1] frontier [2] support [3] error flags
+    unsigned long long *cum;    // [0] edges [1] frontier [2] support [3] sources; never reset by a call
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
     if (SMEM_NXT) {
         for (int i = tid; i < P.n; i += BLOCK) nxt[i] = 0.0;
     }
-    unsigned long long st_edges = 0, st_frontier = 0, st_support = 0;  // thread 0 only
+    unsigned long long st_edges = 0, st_frontier = 0, st_support = 0, st_sources = 0;  // thread 0 only
 
     for (;;) {
         __syncthreads();
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
             for (int i = tid; i < P.K; i += BLOCK) emit(P, it, 0, i, 0, 0.0);
             continue;
         }
-        if (tid == 0) { cur_id[0] = src; cur_val[0] = 1.0; }  // graph.h:80
+        if (tid == 0) { cur_id[0] = src; cur_val[0] = 1.0; st_sources++; }  // graph.h:80
         __syncthreads();
 
         // ------------------------------------------------------------------ push levels
@@ -377,6 +378,10 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         atomicAdd(P.stats + 0, st_edges);
         atomicAdd(P.stats + 1, st_frontier);
         atomicAdd(P.stats + 2, st_support);
+        atomicAdd(P.cum + 0, st_edges);
+        atomicAdd(P.cum + 1, st_frontier);
+        atomicAdd(P.cum + 2, st_support);
+        atomicAdd(P.cum + 3, st_sources);
     }
 }
 
@@ -412,7 +417,7 @@ struct gp_graph {
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
     double *d_coef = nullptr;              // [kMaxLevels]
-    unsigned long long *d_ctrl = nullptr;  // [0] queue, [1..4] stats
+    unsigned long long *d_ctrl = nullptr;  // [0] queue, [1..4] stats, [8..11] cumulative counters
     // staging for the host-buffer entry point
     int *d_node = nullptr;
     size_t d_node_cap = 0;
@@ -573,7 +578,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.sup_id = (int *)(base + pl.off_sup_id);
     P.cand_val = (double *)(base + pl.off_cand);
     P.capF = pl.capF; P.capS = pl.capS;
-    P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1;
+    P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 8;
     rc = pl.block == 256 ? launch_push<256>(P, pl, stream)
          : pl.block == 512 ? launch_push<512>(P, pl, stream)
                            : launch_push<1024>(P, pl, stream);
@@ -603,10 +608,10 @@ int graph_finish_create(gp_graph *g) {
     g->smem_optin = prop.sharedMemPerBlockOptin;
     GP_CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     GP_CUDA_TRY(cudaMalloc(&g->d_coef, sizeof(double) * kMaxLevels));
-    GP_CUDA_TRY(cudaMalloc(&g->d_ctrl, sizeof(unsigned long long) * 8));
+    GP_CUDA_TRY(cudaMalloc(&g->d_ctrl, sizeof(unsigned long long) * 16));
     // validate the CSR once, on the device (the reference validates nothing)
     int *d_flag = (int *)(g->d_ctrl);
-    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 8, g->stream));
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 16, g->stream));
     validate_csr_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(g->d_indptr, g->n, g->d_indices, g->nnz, d_flag);
     GP_CUDA_TRY(cudaGetLastError());
     int flag = 0;
@@ -730,6 +735,20 @@ int gp_gfpush(gp_graph *g, const int32_t *node_idx, int64_t S, const double *coe
     GP_CUDA_TRY(cudaMemcpyAsync(row_idx, d_row, slots * 4, cudaMemcpyDeviceToHost, g->stream));
     GP_CUDA_TRY(cudaMemcpyAsync(col_idx, d_col, slots * 4, cudaMemcpyDeviceToHost, g->stream));
     return collect_stats(g, g->stream);
+}
+
+int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset) {
+    GP_REQUIRE(g && out, "null argument");
+    std::lock_guard<std::mutex> lk(g->mu);
+    DeviceGuard guard(g->device);
+    GP_CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long h[4];
+    GP_CUDA_TRY(cudaMemcpy(h, g->d_ctrl + 8, sizeof h, cudaMemcpyDeviceToHost));
+    if (reset) GP_CUDA_TRY(cudaMemset(g->d_ctrl + 8, 0, sizeof h));
+    *out = g->last;
+    out->edges_pushed = (int64_t)h[0]; out->frontier_total = (int64_t)h[1];
+    out->support_total = (int64_t)h[2]; out->sources = (int64_t)h[3];
+    return GP_OK;
 }
 
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out) {

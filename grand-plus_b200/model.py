@@ -276,6 +276,26 @@ def emb(weight, attr_idx, node_idx, attr_data, input_droprate=0.0, training=Fals
     return out[0]
 
 
+def aggregate_slots(features: DeviceFeatures, col, val32, slot_rows=None, dropnode_rate=0.5, training=True,
+                    n_aug=None, seed=None, offset=None, mask=None, return_mask=False):
+    """Aggregate straight from GFPush's [S,K] output slots (col int32, val fp32) on the device:
+    output row b reads slots ``slot_rows[b]*K .. +K`` (b itself when slot_rows is None); zero pads
+    and rows with a negative slot id contribute nothing."""
+    _need_cuda(features.data, col, val32, slot_rows, mask)
+    S, K = int(col.shape[0]), int(col.shape[1])
+    B = S if slot_rows is None else int(slot_rows.numel())
+    A = 1 if n_aug is None else int(n_aug)
+    if seed is None or offset is None:
+        st = _seed_state()
+        seed, offset = st.seed, st.next()
+    if mask is not None:
+        mask = mask.to(torch.uint8).reshape(A, -1).contiguous()
+    out, m, _ = _launch_fwd(features.data, features.F, features.ld, None, slot_rows, K, col, val32, B, S * K,
+                            float(dropnode_rate), bool(training), A, seed, offset, mask, bool(return_mask),
+                            EPS_RANDOM_PROP, False)
+    return _finish(out, m, n_aug, return_mask)
+
+
 class PiMatrix:
     """Device-resident top-k propagation matrix.
 
@@ -313,16 +333,8 @@ class PiMatrix:
         rows = self.slot_rows(batch_nodes) if slot_rows is None else slot_rows
         if validate and bool((rows < 0).any().item()):
             raise IndexError("batch contains a node that is not a GFPush source")
-        A = 1 if n_aug is None else int(n_aug)
-        if seed is None or offset is None:
-            st = _seed_state()
-            seed, offset = st.seed, st.next()
-        if mask is not None:
-            mask = mask.to(torch.uint8).reshape(A, -1).contiguous()
-        out, m, _ = _launch_fwd(features.data, features.F, features.ld, None, rows, self.K, self.col, self.val,
-                                int(rows.numel()), self.S * self.K, float(dropnode_rate), bool(training), A, seed,
-                                offset, mask, bool(return_mask), EPS_RANDOM_PROP, False)
-        return _finish(out, m, n_aug, return_mask)
+        return aggregate_slots(features, self.col, self.val, rows, dropnode_rate, training, n_aug, seed, offset,
+                               mask, return_mask)
 
     def to_scipy(self, n_nodes=None):
         """The host CSR the reference builds (model.py:270-272), for interop and tests."""

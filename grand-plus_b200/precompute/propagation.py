@@ -142,6 +142,12 @@ class Graph:
         return st.as_dict()
 
 
+    def cumulative_stats(self, reset=False) -> dict:
+        st = _lib.PushStats()
+        _lib.check(self._lib.gp_gfpush_cumulative_stats(self._h, ctypes.byref(st), int(bool(reset))))
+        return st.as_dict()
+
+
 def _current_device() -> int:
     try:
         import torch

@@ -107,6 +107,9 @@ typedef struct {
     int32_t kernel_launches; /* kernels launched by the call                          */
 } gp_push_stats;
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out);
+/* Counters summed over every gfpush since creation / the last reset (device-wide synchronise);
+ * lets a caller time a burst of asynchronous calls and read the work afterwards. */
+int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Part 2: fused gather - mask - scale - reduce aggregation (all pointers DEVICE)
