@@ -35,8 +35,17 @@ constexpr int kHistBins = 2048;     // 11-bit radix digits
 constexpr int kBucketCap = 512;     // boundary bucket resolved in shared memory
 constexpr int kMaxK = kBucketCap;   // K above this is refused
 constexpr int kMaxLevels = 256;
-constexpr unsigned long long kUnseen = ~0ull;  // rsv sentinel: bit pattern of a NaN no sum can produce
 constexpr int kEdgeUnroll = 4;
+constexpr int kSettleUnroll = 4;
+
+// One direct-addressed table slot.  The reserve itself is NOT in the table: a slot only remembers
+// where the node sits in the compact (sup_id, sup_val) arrays, and an epoch tag (= source number)
+// says whether that position belongs to the current source, so nothing is ever reset.
+struct __align__(16) Slot {
+    double nxt;
+    int epoch;
+    int pos;
+};
 
 struct PushParams {
     const int *indptr;
@@ -53,13 +62,15 @@ struct PushParams {
     double *out_val;
     float *out_val32;  // nullable
     // per-CTA scratch
-    double *nxt_slab;  // [ctas][n]   (HBM mode; unused in SMEM mode)
-    double *rsv_slab;  // [ctas][n]   all words == kUnseen between sources
-    int *cur_id;       // [ctas][capF]
-    double *cur_val;   // [ctas][capF]
-    int *nxt_id;       // [ctas][capF]
-    int *sup_id;       // [ctas][capS]
-    double *cand_val;  // [ctas][capS]
+    Slot *tab;         // HBM mode: [ctas][n] 16-byte slots {next residue, epoch, support position}
+    int2 *meta;        // SMEM mode: [ctas][n] {epoch, support position} (next residue lives in shared memory)
+    int epoch_base;    // slot.epoch == epoch_base + it + 1  <=>  node already in source `it`'s reserve
+    int *push_start;   // [ctas][capF]  frontier nodes that passed the threshold: CSR offset (-1 = dangling -> source)
+    int *push_deg;     // [ctas][capF]
+    double *push_val;  // [ctas][capF]  r/deg
+    int *nxt_id;       // [ctas][capF]  ids of the next frontier (first-touch order)
+    int *sup_id;       // [ctas][capS]  reserve support: node ids ...
+    double *sup_val;   // [ctas][capS]  ... and reserve values, compact (first-touch order)
     long long capF, capS;
     unsigned long long *queue;  // [1] next source
     unsigned long long *stats;  // [0] edges [1] frontier [2] support [3] error flags
@@ -78,38 +89,35 @@ struct PushSmem {
     unsigned long long bkey[kBucketCap];
     int bid[kBucketCap];
     long long it;
-    int n_cur, n_nxt, n_sup, n_out, n_bucket;
+    int n_push, n_nxt, n_sup, n_out, n_bucket;
     int sel_bin, sel_above, sel_inbin;
 };
 
-__device__ __forceinline__ double atomic_add_ret(double *p, double v) { return atomicAdd(p, v); }
-
-// Append ids flagged by `is_new` to list[0..cap) through one shared counter per warp.
-// Must be called by all 32 lanes.
-__device__ __forceinline__ void warp_append(bool is_new, int id, int *list, long long cap, int *s_count,
-                                            unsigned long long *err) {
+// Append ids flagged by `is_new` to list[0..cap) through one shared counter per warp; returns the
+// position (or -1).  Must be called by all 32 lanes.
+__device__ __forceinline__ long long warp_append_pos(bool is_new, long long cap, int *s_count,
+                                                     unsigned long long *err) {
     const unsigned m = __ballot_sync(0xffffffffu, is_new);
-    if (m == 0) return;
+    if (m == 0) return -1;
     const int lane = gp_lane();
     const int leader = __ffs(m) - 1;
     int base = 0;
     if (lane == leader) base = atomicAdd(s_count, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (is_new) {
-        long long pos = base + __popc(m & ((1u << lane) - 1u));
-        if (pos < cap) list[pos] = id;
-        else atomicOr(err, kErrOverflow);
-    }
+    if (!is_new) return -1;
+    const long long pos = base + __popc(m & ((1u << lane) - 1u));
+    if (pos >= cap) { atomicOr(err, kErrOverflow); return -1; }
+    return pos;
 }
 
 // Largest t in [0, BLOCK) with off[t] <= e (off is a non-decreasing exclusive scan, off[0] == 0).
 template <int BLOCK>
 __device__ __forceinline__ int owner_of_edge(const unsigned *off, unsigned e) {
-    int lo = 0, hi = BLOCK;  // invariant: off[lo] <= e, (hi == BLOCK or off[hi] > e)
+    int lo = 0;
 #pragma unroll
     for (int step = BLOCK / 2; step >= 1; step >>= 1) {
-        int mid = lo + step;
-        if (mid < hi && off[mid] <= e) lo = mid;
+        const int mid = lo + step;
+        if (off[mid] <= e) lo = mid;   // mid <= BLOCK-1 always: lo + step never exceeds BLOCK-1
     }
     return lo;
 }
@@ -154,25 +162,62 @@ __device__ __forceinline__ void emit(const PushParams &P, long long it, int src,
     if (P.out_val32) P.out_val32[o] = (float)v;
 }
 
+// Per-CTA view of the next-residue table.
+template <bool SMEM_NXT>
+struct Tables {
+    Slot *tab;      // HBM mode
+    int2 *meta;     // SMEM mode
+    double *s_nxt;  // SMEM mode
+    // next[v] += x; true when v had no residue yet (first touch at this level)
+    __device__ __forceinline__ bool add_next(int v, double x) const {
+        double *p = SMEM_NXT ? (s_nxt + v) : &tab[v].nxt;
+        return atomicAdd(p, x) == 0.0;  // graph.h:98
+    }
+    // Takes next[v] (leaving 0).  pos >= 0: v already has a reserve entry at that position.
+    __device__ __forceinline__ double take(int v, int epoch, int &pos) const {
+        if (SMEM_NXT) {
+            const double x = s_nxt[v];
+            s_nxt[v] = 0.0;
+            const int2 m = meta[v];
+            pos = (m.x == epoch) ? m.y : -1;
+            return x;
+        } else {
+            const double4 *unused = nullptr; (void)unused;
+            // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
+            const int4 raw = __ldcg(reinterpret_cast<const int4 *>(tab + v));
+            pos = (raw.z == epoch) ? raw.w : -1;
+            return __hiloint2double(raw.y, raw.x);
+        }
+    }
+    // Clears next[v] and records (epoch, pos): one 16-byte write (HBM) / 8-byte write (SMEM).
+    __device__ __forceinline__ void put(int v, int epoch, int pos, bool changed) const {
+        if (SMEM_NXT) { if (changed) meta[v] = make_int2(epoch, pos); }
+        else *reinterpret_cast<int4 *>(tab + v) = make_int4(0, 0, epoch, pos);
+    }
+};
+
 template <int BLOCK, bool SMEM_NXT>
-__global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams P) {
     __shared__ PushSmem<BLOCK> sm;
     extern __shared__ double s_nxt_dyn[];
 
     const int tid = threadIdx.x;
     const int lane = gp_lane();
     const long long cta = blockIdx.x;
-    double *nxt = SMEM_NXT ? s_nxt_dyn : P.nxt_slab + cta * (long long)P.n;
-    double *rsv = P.rsv_slab + cta * (long long)P.n;
-    int *cur_id = P.cur_id + cta * P.capF;
-    double *cur_val = P.cur_val + cta * P.capF;
+    Tables<SMEM_NXT> T;
+    T.tab = SMEM_NXT ? nullptr : P.tab + cta * (long long)P.n;
+    T.meta = SMEM_NXT ? P.meta + cta * (long long)P.n : nullptr;
+    T.s_nxt = s_nxt_dyn;
+    int *push_start = P.push_start + cta * P.capF;
+    int *push_deg = P.push_deg + cta * P.capF;
+    double *push_val = P.push_val + cta * P.capF;
     int *nxt_id = P.nxt_id + cta * P.capF;
     int *sup_id = P.sup_id + cta * P.capS;
-    double *cand_val = P.cand_val + cta * P.capS;
+    double *sup_val = P.sup_val + cta * P.capS;
     unsigned long long *err = P.stats + 3;
 
     if (SMEM_NXT) {
-        for (int i = tid; i < P.n; i += BLOCK) nxt[i] = 0.0;
+        for (int i = tid; i < P.n; i += BLOCK) s_nxt_dyn[i] = 0.0;
     }
     unsigned long long st_edges = 0, st_frontier = 0, st_support = 0, st_sources = 0;  // thread 0 only
 
@@ -180,7 +225,7 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         __syncthreads();
         if (tid == 0) {
             sm.it = (long long)atomicAdd(P.queue, 1ull);
-            sm.n_cur = 1; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0;
+            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0;
         }
         __syncthreads();
         const long long it = sm.it;
@@ -191,48 +236,37 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
             for (int i = tid; i < P.K; i += BLOCK) emit(P, it, 0, i, 0, 0.0);
             continue;
         }
-        if (tid == 0) { cur_id[0] = src; cur_val[0] = 1.0; st_sources++; }  // graph.h:80
+        const int epoch = P.epoch_base + (int)it + 1;
+        // level 0: residue = {src: 1}, reserve = {src: 0} (graph.h:80-81); settle it right away
+        if (tid == 0) {
+            st_sources++; st_frontier++;
+            T.put(src, epoch, 0, true);
+            sup_id[0] = src; sup_val[0] = P.coef[0]; sm.n_sup = 1;
+            if (P.L > 1) {
+                const int a = P.indptr[src], b = P.indptr[src + 1];
+                const unsigned d = (unsigned)(b - a);
+                if (d == 0) { push_start[0] = -1; push_deg[0] = 1; push_val[0] = 1.0; sm.n_push = 1; }
+                else if (1.0 >= P.rmax * (double)d) { push_start[0] = a; push_deg[0] = (int)d; push_val[0] = 1.0 / (double)d; sm.n_push = 1; }
+            }
+        }
         __syncthreads();
 
-        // ------------------------------------------------------------------ push levels
         for (int level = 0; level < P.L - 1; level++) {  // graph.h:83
-            const int n_cur = sm.n_cur;
-            const double c = P.coef[level];
-            if (tid == 0) st_frontier += n_cur;
-            for (int base = 0; base < n_cur; base += BLOCK) {
+            // ---------------------------------------------------------------- expand (graph.h:94-100)
+            // Only nodes that passed r >= rmax*deg are in the push list.  A tile of BLOCK of them is
+            // prefix-summed by degree and the tile's edges are dealt to threads by rank.
+            const int n_push = sm.n_push;
+            for (int base = 0; base < n_push; base += BLOCK) {
                 const int j = base + tid;
                 unsigned d_push = 0;
                 int start = 0;
                 double val = 0.0;
-                bool new_sup = false;
-                int u = 0;
-                bool dangling = false;
-                double r = 0.0;
-                if (j < n_cur) {
-                    u = cur_id[j];
-                    r = cur_val[j];
-                    double old = rsv[u];
-                    if (__double_as_longlong(old) == (long long)kUnseen) { old = 0.0; new_sup = true; }
-                    rsv[u] = old + c * r;  // graph.h:90 (credited before the threshold test)
-                    const int a = P.indptr[u], b = P.indptr[u + 1];
-                    const unsigned d = (unsigned)(b - a);
-                    if (d == 0) dangling = true;            // graph.h:91-93
-                    else if (r >= P.rmax * (double)d) {     // graph.h:94
-                        d_push = d; start = a; val = r / (double)d;  // graph.h:95
-                    }
-                }
-                warp_append(new_sup, u, sup_id, P.capS, &sm.n_sup, err);
-                {
-                    bool is_new = false;
-                    if (dangling) is_new = (atomic_add_ret(&nxt[src], r) == 0.0);
-                    warp_append(is_new, src, nxt_id, P.capF, &sm.n_nxt, err);
-                }
+                if (j < n_push) { d_push = (unsigned)push_deg[j]; start = push_start[j]; val = push_val[j]; }
                 unsigned total;
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
                 __syncthreads();
                 if (tid == 0) st_edges += total;
-                // edges of the tile, dealt by rank: warp w takes chunks of 32*kEdgeUnroll edges
                 for (unsigned e0 = (unsigned)(tid >> 5) * (32u * kEdgeUnroll); e0 < total;
                      e0 += (BLOCK / 32) * (32u * kEdgeUnroll)) {
                     int v[kEdgeUnroll];
@@ -242,54 +276,86 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         const unsigned e = e0 + q * 32u + lane;
                         ok[q] = e < total;
-                        v[q] = 0; add[q] = 0.0;
+                        v[q] = src; add[q] = 0.0;
                         if (ok[q]) {
                             const int t = owner_of_edge<BLOCK>(sm.off, e);
-                            v[q] = __ldg(P.indices + sm.start[t] + (e - sm.off[t]));  // graph.h:96-97
+                            const int st = sm.start[t];
                             add[q] = sm.val[t];
+                            if (st >= 0) v[q] = __ldg(P.indices + st + (e - sm.off[t]));  // graph.h:96-97
                         }
                     }
                     bool fresh[kEdgeUnroll];
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++)
-                        fresh[q] = ok[q] && (atomic_add_ret(&nxt[v[q]], add[q]) == 0.0);  // graph.h:98
+                    for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next(v[q], add[q]);
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++)
-                        warp_append(fresh[q], v[q], nxt_id, P.capF, &sm.n_nxt, err);
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        const long long pos = warp_append_pos(fresh[q], P.capF, &sm.n_nxt, err);
+                        if (pos >= 0) nxt_id[pos] = v[q];
+                    }
                 }
                 __syncthreads();
             }
-            // residue = next (graph.h:102): drain the table through the id list, leaving it zeroed
+            if (n_push == 0) __syncthreads();
+            // ---------------------------------------------------------------- settle (graph.h:85-93,102)
+            // Every node of the new frontier, independently: take its residue, credit the reserve,
+            // and decide now whether it will push at the next level.
             const int n_nxt = min((long long)sm.n_nxt, P.capF);
-            for (int j = tid; j < n_nxt; j += BLOCK) {
-                const int v = nxt_id[j];
-                double x;
-                if (SMEM_NXT) { x = nxt[v]; nxt[v] = 0.0; }
-                else x = __longlong_as_double((long long)atomicExch((unsigned long long *)&nxt[v], 0ull));
-                cur_id[j] = v;
-                cur_val[j] = x;
-            }
+            const int next_level = level + 1;
+            const bool will_push = next_level < P.L - 1;
+            const double c = P.coef[next_level];
+            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
             __syncthreads();
-            if (tid == 0) { sm.n_cur = n_nxt; sm.n_nxt = 0; }
-            __syncthreads();
-        }
-        // ------------------------------------------------------------------ last level, graph.h:104-110
-        {
-            const int n_cur = sm.n_cur;
-            const double c = P.coef[P.L - 1];
-            if (tid == 0) st_frontier += n_cur;
-            for (int base = 0; base < n_cur; base += BLOCK) {
-                const int j = base + tid;
-                bool new_sup = false;
-                int u = 0;
-                if (j < n_cur) {
-                    u = cur_id[j];
-                    double old = rsv[u];
-                    if (__double_as_longlong(old) == (long long)kUnseen) { old = 0.0; new_sup = true; }
-                    rsv[u] = old + c * cur_val[j];
+            for (int base = 0; base < n_nxt; base += BLOCK * kSettleUnroll) {
+                int v[kSettleUnroll];
+                bool ok[kSettleUnroll];
+                int a[kSettleUnroll], b[kSettleUnroll];
+#pragma unroll
+                for (int q = 0; q < kSettleUnroll; q++) {
+                    const int j = base + q * BLOCK + tid;
+                    ok[q] = j < n_nxt;
+                    v[q] = ok[q] ? nxt_id[j] : 0;
                 }
-                warp_append(new_sup, u, sup_id, P.capS, &sm.n_sup, err);
+                double x[kSettleUnroll];
+                int pos[kSettleUnroll];
+#pragma unroll
+                for (int q = 0; q < kSettleUnroll; q++) {
+                    pos[q] = 0; x[q] = 0.0;
+                    if (ok[q]) x[q] = T.take(v[q], epoch, pos[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < kSettleUnroll; q++) {
+                    a[q] = 0; b[q] = 0;
+                    if (ok[q] && will_push) { a[q] = __ldg(P.indptr + v[q]); b[q] = __ldg(P.indptr + v[q] + 1); }
+                }
+#pragma unroll
+                for (int q = 0; q < kSettleUnroll; q++) {
+                    // reserve[v] += coef * r (graph.h:90), in the compact support arrays
+                    const bool first = ok[q] && pos[q] < 0;
+                    const long long ps = warp_append_pos(first, P.capS, &sm.n_sup, err);
+                    if (first) {
+                        if (ps >= 0) { sup_id[ps] = v[q]; sup_val[ps] = c * x[q]; }
+                        T.put(v[q], epoch, (int)max(ps, 0ll), true);
+                    } else if (ok[q]) {
+                        sup_val[pos[q]] += c * x[q];
+                        T.put(v[q], epoch, pos[q], false);
+                    }
+                    bool push = false;
+                    int st = -1, dg = 1;
+                    double val = x[q];
+                    if (ok[q] && will_push) {
+                        const unsigned d = (unsigned)(b[q] - a[q]);
+                        if (d == 0) push = true;                                   // graph.h:91-93: back to the source
+                        else if (x[q] >= P.rmax * (double)d) {                     // graph.h:94
+                            push = true; st = a[q]; dg = (int)d; val = x[q] / (double)d;  // graph.h:95
+                        }
+                    }
+                    const long long pp = warp_append_pos(push, P.capF, &sm.n_push, err);
+                    if (pp >= 0) { push_start[pp] = st; push_deg[pp] = dg; push_val[pp] = val; }
+                }
             }
+            __syncthreads();
+            if (tid == 0) sm.n_nxt = 0;
+            __syncthreads();
         }
         for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
         __syncthreads();
@@ -297,12 +363,9 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         // ------------------------------------------------------------------ top-k, graph.h:111-126
         const int n_sup = min((long long)sm.n_sup, P.capS);
         if (tid == 0) st_support += n_sup;
-        // pass 0: move the reserve out of the table (restoring the sentinel) + exponent histogram
+        // pass 0: exponent histogram of the compact reserve values (coalesced; no table access)
         for (int j = tid; j < n_sup; j += BLOCK) {
-            const int u = sup_id[j];
-            const double x = rsv[u];
-            reinterpret_cast<unsigned long long *>(rsv)[u] = kUnseen;
-            cand_val[j] = x;
+            const double x = sup_val[j];
             if (x > 0.0) atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u);
         }
         __syncthreads();
@@ -310,27 +373,25 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         unsigned long long prefix = 0;  // value of key >> (shift+bits) shared by the boundary bucket
         int kk = P.K;
         bool first = true;
-        int n_above_total = 0;
-        unsigned long long T = 0;
+        unsigned long long Tkey = 0;
         int want_bucket = 0;
         for (;;) {
             const unsigned total = select_bin<BLOCK>(sm, 1 << bits, kk, first);
             if (first) kk = min(kk, (int)total);  // k = min(K, #positive): graph.h:113 + the v>0 filter of :121
-            if (kk == 0) { want_bucket = 0; T = ~0ull; break; }
+            if (kk == 0) { want_bucket = 0; Tkey = ~0ull; break; }
             const int bin = sm.sel_bin, above = sm.sel_above, inbin = sm.sel_inbin;
-            T = (prefix << bits) | (unsigned long long)bin;
-            n_above_total += above;
+            Tkey = (prefix << bits) | (unsigned long long)bin;
             want_bucket = kk - above;
             if (inbin <= kBucketCap || shift == 0) break;
             // refine inside the boundary bucket on the next digit
-            kk = want_bucket; first = false; prefix = T;
+            kk = want_bucket; first = false; prefix = Tkey;
             __syncthreads();
             for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
             __syncthreads();
             const int nshift = shift >= 11 ? shift - 11 : 0;
             const int nbits = shift >= 11 ? 11 : shift;
             for (int j = tid; j < n_sup; j += BLOCK) {
-                const double x = cand_val[j];
+                const double x = sup_val[j];
                 if (x > 0.0) {
                     const unsigned long long key = (unsigned long long)__double_as_longlong(x);
                     if ((key >> shift) == prefix)
@@ -342,13 +403,13 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         }
         // final pass: everything above the boundary bucket is selected; the bucket goes to smem
         for (int j = tid; j < n_sup; j += BLOCK) {
-            const double x = cand_val[j];
+            const double x = sup_val[j];
             if (x > 0.0) {
                 const unsigned long long key = (unsigned long long)__double_as_longlong(x);
                 const unsigned long long t = key >> shift;
-                if (t > T) {
+                if (t > Tkey) {
                     emit(P, it, src, atomicAdd(&sm.n_out, 1), sup_id[j], x);
-                } else if (t == T) {
+                } else if (t == Tkey) {
                     const int pos = atomicAdd(&sm.n_bucket, 1);
                     if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = sup_id[j]; }
                 }
@@ -372,7 +433,6 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         __syncthreads();
         // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
         for (int i = sm.n_out + tid; i < P.K; i += BLOCK) emit(P, it, 0, i, 0, 0.0);
-        (void)n_above_total;
     }
     if (tid == 0) {
         atomicAdd(P.stats + 0, st_edges);
@@ -382,6 +442,15 @@ __global__ void __launch_bounds__(BLOCK) gfpush_kernel(PushParams P) {
         atomicAdd(P.cum + 1, st_frontier);
         atomicAdd(P.cum + 2, st_support);
         atomicAdd(P.cum + 3, st_sources);
+    }
+}
+
+// Table invariant between sources: next residue 0; epoch 0 never matches a source (epochs start at 1).
+__global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        if (tab16) tab16[i] = make_int4(0, 0, 0, 0);
+        else meta8[i] = make_int2(0, 0);
     }
 }
 
@@ -416,6 +485,7 @@ struct gp_graph {
     size_t scratch_bytes = 0;
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
+    long long epoch_base = 0;              // sources pushed since the tables were last initialised
     double *d_coef = nullptr;              // [kMaxLevels]
     unsigned long long *d_ctrl = nullptr;  // [0] queue, [1..4] stats, [8..11] cumulative counters
     // staging for the host-buffer entry point
@@ -450,12 +520,15 @@ struct Plan {
     long long ctas, capF, capS;
     size_t dyn_smem;
     size_t bytes;
-    size_t off_nxt, off_rsv, off_cur_id, off_cur_val, off_nxt_id, off_sup_id, off_cand;
+    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand;
 };
 
 int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     const long long n = g->n;
-    int block = g->cfg.block_threads ? g->cfg.block_threads : 512;
+    // Measured on B200 (profiles/r01_block_sweep.md): one 1024-thread CTA per SM wins whenever a source
+    // carries thousands of frontier nodes (fewer concurrent sources -> their table lines stay in L2);
+    // tiny graphs (Cora-sized) prefer four 256-thread CTAs per SM because their levels are sync-bound.
+    int block = g->cfg.block_threads ? g->cfg.block_threads : (n <= 4096 ? 256 : 1024);
     GP_REQUIRE(block == 256 || block == 512 || block == 1024, "block_threads must be 256, 512 or 1024 (got %d)", block);
     const size_t stat = block == 256 ? static_smem_bytes<256>() : block == 512 ? static_smem_bytes<512>() : static_smem_bytes<1024>();
     const size_t smem_need = stat + (size_t)n * sizeof(double) + 1024;
@@ -484,13 +557,13 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         const int fit = std::max(1, (int)(((size_t)228 * 1024) / smem_need));  // 228 KB of smem per SM
         per_sm = std::min(per_sm, fit);
     }
-    long long ctas = std::min<long long>((long long)g->num_sms * per_sm, std::max<long long>(S, 1));
+    long long ctas = (long long)g->num_sms * per_sm;  // scratch is sized for a full grid; small calls launch fewer
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
-        p->off_nxt = o; if (mode == GP_SCRATCH_HBM) o += align_up((size_t)c * n * 8, 256);
-        p->off_rsv = o; o += align_up((size_t)c * n * 8, 256);
-        p->off_cur_id = o; o += align_up((size_t)c * capF * 4, 256);
-        p->off_cur_val = o; o += align_up((size_t)c * capF * 8, 256);
+        p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 8), 256);
+        p->off_push_start = o; o += align_up((size_t)c * capF * 4, 256);
+        p->off_push_deg = o; o += align_up((size_t)c * capF * 4, 256);
+        p->off_push_val = o; o += align_up((size_t)c * capF * 8, 256);
         p->off_nxt_id = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_sup_id = o; o += align_up((size_t)c * capS * 4, 256);
         p->off_cand = o; o += align_up((size_t)c * capS * 8, 256);
@@ -511,9 +584,10 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     return GP_OK;
 }
 
-int ensure_scratch(gp_graph *g, const Plan &pl, cudaStream_t stream) {
+int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream) {
     const bool same = g->scratch && g->scratch_bytes >= pl.bytes && g->scratch_ctas == pl.ctas &&
-                      g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode;
+                      g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode &&
+                      g->epoch_base + S < (1ll << 31) - 2;  // epoch tags are int32: re-initialise before they wrap
     if (same) return GP_OK;
     if (g->scratch && g->scratch_bytes < pl.bytes) {
         GP_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -524,11 +598,13 @@ int ensure_scratch(gp_graph *g, const Plan &pl, cudaStream_t stream) {
         GP_CUDA_TRY(cudaMalloc(&g->scratch, pl.bytes));
         g->scratch_bytes = pl.bytes;
     }
-    // table invariants between sources: nxt == 0 everywhere, rsv == kUnseen everywhere
+    // table invariants between sources: next residue == 0 everywhere, reserve == kUnseen everywhere
     char *base = (char *)g->scratch;
-    if (pl.mode == GP_SCRATCH_HBM)
-        GP_CUDA_TRY(cudaMemsetAsync(base + pl.off_nxt, 0, (size_t)pl.ctas * g->n * 8, stream));
-    GP_CUDA_TRY(cudaMemsetAsync(base + pl.off_rsv, 0xFF, (size_t)pl.ctas * g->n * 8, stream));
+    init_tables_kernel<<<g->num_sms * 8, 256, 0, stream>>>(
+        pl.mode == GP_SCRATCH_HBM ? (int4 *)(base + pl.off_tab) : nullptr,
+        pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n);
+    GP_CUDA_TRY(cudaGetLastError());
+    g->epoch_base = 0;
     g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
     return GP_OK;
 }
@@ -540,9 +616,9 @@ int launch_push(const PushParams &P, const Plan &pl, cudaStream_t stream) {
                                          (int)pl.dyn_smem));
         GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
-        gfpush_kernel<BLOCK, true><<<(unsigned)pl.ctas, BLOCK, pl.dyn_smem, stream>>>(P);
+        gfpush_kernel<BLOCK, true><<<(unsigned)std::min<long long>(pl.ctas, P.S), BLOCK, pl.dyn_smem, stream>>>(P);
     } else {
-        gfpush_kernel<BLOCK, false><<<(unsigned)pl.ctas, BLOCK, 0, stream>>>(P);
+        gfpush_kernel<BLOCK, false><<<(unsigned)std::min<long long>(pl.ctas, P.S), BLOCK, 0, stream>>>(P);
     }
     GP_CUDA_TRY(cudaGetLastError());
     return GP_OK;
@@ -561,7 +637,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     Plan pl{};
     int rc = make_plan(g, S, L, rmax, &pl);
     if (rc != GP_OK) return rc;
-    rc = ensure_scratch(g, pl, stream);
+    rc = ensure_scratch(g, pl, S, stream);
     if (rc != GP_OK) return rc;
     GP_CUDA_TRY(cudaMemcpyAsync(g->d_coef, coef, sizeof(double) * L, cudaMemcpyHostToDevice, stream));
     GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 8, stream));
@@ -570,20 +646,23 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.indptr = g->d_indptr; P.indices = g->d_indices; P.n = (int)g->n;
     P.node_idx = d_node_idx; P.S = S; P.coef = g->d_coef; P.L = L; P.rmax = rmax; P.K = K;
     P.out_row = d_row; P.out_col = d_col; P.out_val = d_val; P.out_val32 = d_val32;
-    P.nxt_slab = (double *)(base + pl.off_nxt);
-    P.rsv_slab = (double *)(base + pl.off_rsv);
-    P.cur_id = (int *)(base + pl.off_cur_id);
-    P.cur_val = (double *)(base + pl.off_cur_val);
+    P.tab = (Slot *)(base + pl.off_tab);
+    P.meta = (int2 *)(base + pl.off_tab);
+    P.epoch_base = (int)g->epoch_base;
+    P.push_start = (int *)(base + pl.off_push_start);
+    P.push_deg = (int *)(base + pl.off_push_deg);
+    P.push_val = (double *)(base + pl.off_push_val);
     P.nxt_id = (int *)(base + pl.off_nxt_id);
     P.sup_id = (int *)(base + pl.off_sup_id);
-    P.cand_val = (double *)(base + pl.off_cand);
+    P.sup_val = (double *)(base + pl.off_cand);
     P.capF = pl.capF; P.capS = pl.capS;
     P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 8;
     rc = pl.block == 256 ? launch_push<256>(P, pl, stream)
          : pl.block == 512 ? launch_push<512>(P, pl, stream)
                            : launch_push<1024>(P, pl, stream);
     if (rc != GP_OK) return rc;
-    g->last.sources = S; g->last.ctas = pl.ctas; g->last.scratch_bytes = (int64_t)g->scratch_bytes;
+    g->epoch_base += S;
+    g->last.sources = S; g->last.ctas = std::min<long long>(pl.ctas, S); g->last.scratch_bytes = (int64_t)g->scratch_bytes;
     g->last.scratch_mode = pl.mode; g->last.kernel_launches = 1;
     return GP_OK;
 }
