@@ -44,7 +44,7 @@ WORKLOADS = {
     "reddit": dict(config=2, n=232_965, draws=11_606_919, F=602, mode="ppr", order=6, alpha=0.05, rmax=1e-5, K=32,
                    S=16384),
     "amazon2m": dict(config=3, n=2_449_029, draws=61_859_140, F=100, mode="ppr", order=6, alpha=0.2, rmax=1e-6,
-                     K=64, S=4096),
+                     K=64, S=16384),
     "small": dict(config=-1, n=50_000, draws=600_000, F=64, mode="ppr", order=6, alpha=0.05, rmax=1e-5, K=32, S=2048),
 }
 DROPNODE_P = 0.5   # run_model.py:56 default

@@ -116,7 +116,9 @@ def _launch_fwd(table, F_cols, ld_table, row_ptr, slot_rows, slot_K, nbr, score,
                 seed, offset, mask_in, want_mask, eps, want_denom):
     lib = _lib.load()
     dev = table.device
-    out = torch.empty((n_aug, B, F_cols), dtype=torch.float32, device=dev)
+    # rows padded to a 16-byte multiple so the kernel can use 128-bit stores; callers get the [.., :F] view
+    ld_out = (int(F_cols) + 3) // 4 * 4
+    out = torch.empty((n_aug, B, ld_out), dtype=torch.float32, device=dev)
     mask_out = torch.empty((n_aug, n_entries), dtype=torch.uint8, device=dev) if want_mask else None
     denom = torch.empty((n_aug, B), dtype=torch.float32, device=dev) if want_denom else None
     a = _lib.AggregateArgs()
@@ -130,10 +132,10 @@ def _launch_fwd(table, F_cols, ld_table, row_ptr, slot_rows, slot_K, nbr, score,
     a.seed = int(seed) & (2**64 - 1); a.offset = int(offset) & (2**64 - 1)
     a.mask_in = 0 if mask_in is None else mask_in.data_ptr()
     a.mask_out = 0 if mask_out is None else mask_out.data_ptr()
-    a.eps = float(eps); a.out = out.data_ptr(); a.ld_out = int(F_cols)
+    a.eps = float(eps); a.out = out.data_ptr(); a.ld_out = ld_out
     a.denom_out = 0 if denom is None else denom.data_ptr()
     _lib.check(lib.gp_aggregate_fwd(ctypes.byref(a), _stream(dev)))
-    return out, mask_out, denom
+    return (out if ld_out == F_cols else out[:, :, :F_cols]), mask_out, denom
 
 
 class _AggregateFn(torch.autograd.Function):
