@@ -213,7 +213,8 @@ def run_ours(args):
         out = gm.aggregate_slots(feats, col, val32, None, DROPNODE_P, True, n_aug=N_AUG, seed=1234, offset=i)
         if timed:
             ev[i - args.warmup][2].record()
-        checks.append(out[0, 0, 0])
+        checks.append(out[0, 0, 0].clone())   # a 4-byte copy, not a view: lets the allocator recycle `out`
+        del out, col, val32, _row, _val
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -86,6 +86,7 @@ SIGNATURES = {
     "gp_aggregate_bwd": (ctypes.c_int, [ctypes.POINTER(AggregateBwdArgs), c_vp]),
     "gp_segments_from_sorted_index": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "gp_narrow_index": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp]),
+    "gp_set_tuning": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
     "gp_dropnode_mask": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64,
                                         ctypes.c_uint64, c_vp, c_vp]),
 }
@@ -123,6 +124,10 @@ def check(status: int) -> None:
     if status != GP_OK:
         msg = load().gp_last_error()
         raise GPError(status, msg.decode("utf-8", "replace") if msg else "unknown error")
+
+
+def set_tuning(key: str, value: int) -> None:
+    check(load().gp_set_tuning(key.encode(), int(value)))
 
 
 def require_cuda() -> None:

@@ -18,6 +18,7 @@
 #include "gp_common.cuh"
 
 #include <algorithm>
+#include <string>
 
 namespace {
 
@@ -198,6 +199,159 @@ __global__ void __launch_bounds__(kAggBlock) aggregate_fwd_kernel(AggParams P) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------- TMA-staged forward
+// Same math as aggregate_fwd_kernel, but the kept table rows are staged through shared memory by the
+// TMA unit: one elected lane issues one `cp.async.bulk` (SASS: UBLKCP) per row tile, completion is
+// signalled on a per-slot mbarrier, and every warp runs its own ring of `nbuf` slots.  Bytes in
+// flight are then bounded by shared memory (~190 KB per SM) instead of by registers, and address
+// generation for a 2.4 KB row costs one instruction instead of 5 x 32 LDG.128.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int NCHUNK, int NAUG>
+__global__ void __launch_bounds__(kAggBlock) aggregate_fwd_bulk_kernel(AggParams P, int nbuf, int buf_stride, int warp_stride) {
+    extern __shared__ __align__(128) unsigned char agg_smem[];
+    const int lane = gp_lane();
+    const long long warp = ((long long)blockIdx.x * kAggBlock + threadIdx.x) >> 5;
+    const long long b = warp / P.n_ctile;
+    if (b >= P.B) return;  // warp-uniform; no CTA-wide barrier is used below
+    const int ctile = (int)(warp - b * P.n_ctile);
+    unsigned char *my = agg_smem + (size_t)(threadIdx.x >> 5) * warp_stride;
+    const unsigned buf0 = smem_u32(my);
+    const unsigned bar0 = smem_u32(my + (size_t)nbuf * buf_stride);
+    if (lane == 0) {
+        for (int i = 0; i < nbuf; i++) mbar_init(bar0 + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int Fpad = (P.F + 3) & ~3;
+    const int tile_c0 = ctile * P.tile_cols;
+    const int tile_valid = min(P.tile_cols, Fpad - tile_c0);  // columns of this tile, multiple of 4
+    const unsigned tile_bytes = (unsigned)tile_valid * 4u;
+    const int col_lane = lane * 4;
+
+    long long j0, j1;
+    row_range(P, b, j0, j1);
+
+    float acc[NAUG][NCHUNK][4];
+    float wsum[NAUG];
+#pragma unroll
+    for (int a = 0; a < NAUG; a++) {
+        wsum[a] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; c++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[a][c][k] = 0.0f;
+    }
+    int seq_issue = 0, seq_cons = 0;  // running copy numbers of this warp: slot = seq % nbuf, parity = (seq / nbuf) & 1
+
+    for (long long j = j0; j < j1; j += 32) {
+        const long long jj = j + lane;
+        const bool valid = jj < j1;
+        int my_nbr = 0;
+        float my_m[NAUG];
+        bool any = false;
+        {
+            float s = 0.0f;
+            if (valid) {
+                s = P.score[jj];
+                my_nbr = P.nbr ? P.nbr[jj] : (int)jj;
+            }
+            const bool live = valid && (P.row_ptr != nullptr || s > 0.0f);
+#pragma unroll
+            for (int a = 0; a < NAUG; a++) {
+                bool keep = false;
+                my_m[a] = live ? entry_weight(P, jj, a, s, keep) : 0.0f;
+                if (valid && P.mask_out && ctile == 0) P.mask_out[(long long)a * P.n_entries + jj] = (live && keep) ? 1 : 0;
+                any |= (my_m[a] != 0.0f);
+            }
+        }
+        const unsigned kept = __ballot_sync(0xffffffffu, any);
+        const int n = __popc(kept);
+        int issued = 0;
+        for (int i = 0; i < n; i++) {
+            // keep up to nbuf row copies in flight
+            while (issued < n && issued - i < nbuf) {
+                const int el = __fns(kept, 0, issued + 1);
+                const int nb = __shfl_sync(0xffffffffu, my_nbr, el);
+                if (lane == 0) {
+                    const int slot = seq_issue % nbuf;
+                    mbar_expect_tx(bar0 + 8 * slot, tile_bytes);
+                    bulk_g2s(buf0 + slot * buf_stride, P.table + (long long)nb * P.ld_table + tile_c0, tile_bytes,
+                             bar0 + 8 * slot);
+                }
+                seq_issue++; issued++;
+            }
+            const int el = __fns(kept, 0, i + 1);
+            const int slot = seq_cons % nbuf;
+            mbar_wait(bar0 + 8 * slot, (unsigned)((seq_cons / nbuf) & 1));
+            const float *row = reinterpret_cast<const float *>(my + (size_t)slot * buf_stride);
+            float x[NCHUNK][4];
+#pragma unroll
+            for (int c = 0; c < NCHUNK; c++) {
+                const int col = col_lane + c * 128;
+                if (col < tile_valid) {
+                    const float4 v = *reinterpret_cast<const float4 *>(row + col);
+                    x[c][0] = v.x; x[c][1] = v.y; x[c][2] = v.z; x[c][3] = v.w;
+                } else { x[c][0] = x[c][1] = x[c][2] = x[c][3] = 0.0f; }
+            }
+#pragma unroll
+            for (int a = 0; a < NAUG; a++) {
+                const float m = __shfl_sync(0xffffffffu, my_m[a], el);
+                wsum[a] += m;
+#pragma unroll
+                for (int c = 0; c < NCHUNK; c++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++) acc[a][c][k] = fmaf(m, x[c][k], acc[a][c][k]);
+            }
+            seq_cons++;
+            __syncwarp();  // every lane has consumed the slot before lane 0 may refill it
+        }
+    }
+    const bool out_vec = ((reinterpret_cast<uintptr_t>(P.out) | (uintptr_t)(P.ld_out * 4)) & 15) == 0;
+#pragma unroll
+    for (int a = 0; a < NAUG; a++) {
+        const float den = wsum[a] + P.eps;
+        float *orow = P.out + ((long long)a * P.B + b) * P.ld_out + tile_c0;
+#pragma unroll
+        for (int c = 0; c < NCHUNK; c++) {
+            const int col = col_lane + c * 128;
+            if (col < tile_valid) {
+                float y[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) y[k] = acc[a][c][k] / den;
+                if (out_vec && tile_c0 + col + 4 <= P.ld_out) vec_store<4>(orow + col, y);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) if (tile_c0 + col + k < P.F) orow[col + k] = y[k];
+                }
+            }
+        }
+        if (P.denom_out && ctile == 0 && lane == 0) P.denom_out[(long long)a * P.B + b] = den;
+    }
+}
+
 // ---------------------------------------------------------------------------------- backward
 struct AggBwdParams {
     const float *grad_out;
@@ -325,13 +479,14 @@ __global__ void mask_kernel(long long n, int n_aug, unsigned thresh, int drop_al
 }
 
 // ---------------------------------------------------------------------------------- dispatch
+extern int g_agg_max_vec, g_agg_max_chunk;
 struct Tiling { int vec, nchunk, n_ctile, tile_cols; };
 
 bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 // Widest vector the row starts allow, then the fewest column tiles of <= 4 chunks per lane.
-Tiling choose_tiling(int F, const void *p0, long long ld0, const void *p1, long long ld1) {
-    int vec = 4;
+Tiling choose_tiling(int F, long long B, const void *p0, long long ld0, const void *p1, long long ld1) {
+    int vec = g_agg_max_vec >= 4 ? 4 : g_agg_max_vec >= 2 ? 2 : 1;
     while (vec > 1) {
         const size_t bytes = (size_t)vec * 4;
         if (aligned_to(p0, bytes) && aligned_to(p1, bytes) && ld0 % vec == 0 && ld1 % vec == 0) break;
@@ -339,7 +494,11 @@ Tiling choose_tiling(int F, const void *p0, long long ld0, const void *p1, long 
     }
     while (vec > 1 && 32 * (vec / 2) >= F) vec >>= 1;  // narrow rows: keep all 32 lanes busy
     const int chunks = (F + 32 * vec - 1) / (32 * vec);
-    const int n_ctile = (chunks + 3) / 4;
+    int maxc = std::max(1, std::min(4, g_agg_max_chunk));
+    // small batches (the reference trains with B = 150..250 rows): more column tiles so the launch
+    // still covers the 148 SMs with several warps each
+    while (maxc > 1 && B * ((chunks + maxc - 1) / maxc) < (long long)GP_NUM_SMS_FALLBACK * 16) maxc--;
+    const int n_ctile = (chunks + maxc - 1) / maxc;
     const int nchunk = (chunks + n_ctile - 1) / n_ctile;
     return Tiling{vec, nchunk, n_ctile, nchunk * 32 * vec};
 }
@@ -405,6 +564,74 @@ int launch_bwd_c(const AggBwdParams &P, int nchunk, int n_aug, cudaStream_t s) {
     }
 }
 
+
+// ---- tuning knobs (gp_set_tuning): defaults are the measured best, knobs exist for the sweeps in profiles/
+// Measured (profiles/r01_aggregate_sweep.txt): the register-staged kernel with 64-bit loads wins or ties
+// everywhere -- 128-bit loads cost registers (80 vs 58 -> 24 vs 32 resident warps) and the TMA-staged
+// kernel only ties it on 2.4 KB rows and loses badly on 400-byte rows (one lane issues every copy).
+int g_agg_kernel = 0;     // 0 auto (= 1), 1 register-staged LDG kernel, 2 TMA-staged bulk kernel
+int g_agg_nbuf = 0;       // 0 auto
+int g_agg_max_vec = 2;
+int g_agg_max_chunk = 4;
+int g_agg_smem_kb = 96;   // dynamic shared memory per CTA for the bulk kernel (2 CTAs per SM)
+
+template <int NCHUNK, int NAUG>
+int launch_bulk_t(AggParams P, int nbuf, int buf_stride, int warp_stride, size_t smem, cudaStream_t stream) {
+    const long long warps = P.B * P.n_ctile;
+    const long long blocks = (warps * 32 + kAggBlock - 1) / kAggBlock;
+    GP_REQUIRE(blocks < (1ll << 31), "batch too large for one launch");
+    static size_t configured = 0;
+    if (smem > configured) {
+        GP_CUDA_TRY(cudaFuncSetAttribute(aggregate_fwd_bulk_kernel<NCHUNK, NAUG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    aggregate_fwd_bulk_kernel<NCHUNK, NAUG><<<(unsigned)blocks, kAggBlock, smem, stream>>>(P, nbuf, buf_stride, warp_stride);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+template <int NCHUNK>
+int launch_bulk_a(const AggParams &P, int n_aug, int nbuf, int bs, int ws, size_t smem, cudaStream_t s) {
+    switch (n_aug) {
+        case 1: return launch_bulk_t<NCHUNK, 1>(P, nbuf, bs, ws, smem, s);
+        case 2: return launch_bulk_t<NCHUNK, 2>(P, nbuf, bs, ws, smem, s);
+        case 3: return launch_bulk_t<NCHUNK, 3>(P, nbuf, bs, ws, smem, s);
+        default: return launch_bulk_t<NCHUNK, 4>(P, nbuf, bs, ws, smem, s);
+    }
+}
+
+// Returns 1 when the bulk kernel was launched, 0 when it does not apply, negative on error.
+int try_launch_bulk(AggParams P, int n_aug, cudaStream_t s) {
+    const int Fpad = (P.F + 3) & ~3;
+    if (!aligned_to(P.table, 16) || P.ld_table % 4 != 0 || P.ld_table < Fpad) return 0;
+    const int chunks = (Fpad + 127) / 128;
+    const int n_ctile = (chunks + 7) / 8;
+    const int nchunk = (chunks + n_ctile - 1) / n_ctile;
+    P.n_ctile = n_ctile; P.tile_cols = nchunk * 128;
+    const int tile_bytes = std::min(P.tile_cols, Fpad) * 4;
+    const int buf_stride = (tile_bytes + 127) / 128 * 128;
+    const int warps_per_cta = kAggBlock / 32;
+    const int budget = g_agg_smem_kb * 1024 / warps_per_cta;
+    int nbuf = g_agg_nbuf > 0 ? g_agg_nbuf : std::min(16, (budget - 128) / buf_stride);
+    if (nbuf < 2) return 0;
+    const int warp_stride = (nbuf * buf_stride + nbuf * 8 + 127) / 128 * 128;
+    const size_t smem = (size_t)warp_stride * warps_per_cta;
+    if (smem > 200 * 1024) return 0;
+    int rc;
+    switch (nchunk) {
+        case 1: rc = launch_bulk_a<1>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        case 2: rc = launch_bulk_a<2>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        case 3: rc = launch_bulk_a<3>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        case 4: rc = launch_bulk_a<4>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        case 5: rc = launch_bulk_a<5>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        case 6: rc = launch_bulk_a<6>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        case 7: rc = launch_bulk_a<7>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+        default: rc = launch_bulk_a<8>(P, n_aug, nbuf, buf_stride, warp_stride, smem, s); break;
+    }
+    return rc == GP_OK ? 1 : rc;
+}
+
 void dropout_consts(double p, int training, int *use_mask, float *scale, unsigned *thresh, int *drop_all) {
     *use_mask = (training && p > 0.0) ? 1 : 0;
     *drop_all = (p >= 1.0) ? 1 : 0;
@@ -437,9 +664,14 @@ int gp_aggregate_fwd(const gp_aggregate_args *A, void *stream) {
     P.seed = A->seed; P.offset = A->offset;
     P.mask_in = A->mask_in; P.mask_out = A->mask_out; P.eps = A->eps;
     P.out = A->out; P.ld_out = A->ld_out; P.denom_out = A->denom_out;
-    const Tiling t = choose_tiling(A->F, A->table, A->ld_table, A->out, A->ld_out);
-    P.n_ctile = t.n_ctile; P.tile_cols = t.tile_cols;
     cudaStream_t s = (cudaStream_t)stream;
+    if (g_agg_kernel == 2) {
+        const int rc = try_launch_bulk(P, A->n_aug, s);
+        if (rc != 0) return rc < 0 ? rc : GP_OK;
+        GP_REQUIRE(g_agg_kernel != 2, "bulk kernel forced but the table is not 16-byte aligned / padded");
+    }
+    const Tiling t = choose_tiling(A->F, A->B, A->table, A->ld_table, A->out, A->ld_out);
+    P.n_ctile = t.n_ctile; P.tile_cols = t.tile_cols;
     switch (t.vec) {
         case 4: return launch_fwd_c<4>(P, t.nchunk, A->n_aug, s);
         case 2: return launch_fwd_c<2>(P, t.nchunk, A->n_aug, s);
@@ -463,7 +695,7 @@ int gp_aggregate_bwd(const gp_aggregate_bwd_args *A, void *stream) {
     dropout_consts(A->p, A->training, &P.use_mask, &P.scale, &thresh, &drop_all);
     GP_REQUIRE(!P.use_mask || A->mask_in, "training-mode backward needs the forward pass's mask");
     P.mask_in = A->mask_in; P.grad_table = A->grad_table; P.ld_grad_table = A->ld_grad_table;
-    const Tiling t = choose_tiling(A->F, A->grad_out, A->ld_grad_out, A->grad_table, A->ld_grad_table);
+    const Tiling t = choose_tiling(A->F, A->B, A->grad_out, A->ld_grad_out, A->grad_table, A->ld_grad_table);
     P.n_ctile = t.n_ctile; P.tile_cols = t.tile_cols;
     cudaStream_t s = (cudaStream_t)stream;
     switch (t.vec) {
@@ -490,6 +722,18 @@ int gp_narrow_index(const int64_t *d_idx, int64_t n, int64_t n_rows, int32_t *d_
     const long long blocks = std::min<long long>((n + 255) / 256, 148 * 8);
     narrow_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const long long *)d_idx, n, n_rows, d_out, d_flags);
     GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+int gp_set_tuning(const char *key, int64_t value) {
+    GP_REQUIRE(key != nullptr, "key is null");
+    const std::string k(key);
+    if (k == "agg_kernel") g_agg_kernel = (int)value;
+    else if (k == "agg_nbuf") g_agg_nbuf = (int)value;
+    else if (k == "agg_max_vec") g_agg_max_vec = (int)value;
+    else if (k == "agg_max_chunk") g_agg_max_chunk = (int)value;
+    else if (k == "agg_smem_kb") g_agg_smem_kb = (int)value;
+    else { gp_set_error("unknown tuning key '%s'", key); return GP_ERR_INVALID; }
     return GP_OK;
 }
 

@@ -186,6 +186,11 @@ int gp_narrow_index(const int64_t *d_idx, int64_t n, int64_t n_rows, int32_t *d_
 int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, uint64_t offset,
                      uint8_t *d_mask, void *stream);
 
+/* Performance knobs for sweeps (profiles/); defaults are the measured best.  Keys: "agg_kernel"
+ * (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf", "agg_max_vec",
+ * "agg_max_chunk", "agg_smem_kb".  Results never depend on them. */
+int gp_set_tuning(const char *key, int64_t value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Sweep the aggregation kernels on a B200: register-staged LDG kernel vs TMA-staged bulk kernel.
+Prints algorithmic GB/s (SURVEY 8d bytes) per configuration.  Usage: python tools/bench_aggregate.py"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from grandplus_b200 import _lib, model as gm, synth  # noqa: E402
+
+_pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+PEAK = json.load(open(_pk))["hbm_gbs"] if os.path.exists(_pk) else 6650.0
+DEFAULTS = dict(agg_kernel=0, agg_nbuf=0, agg_max_vec=2, agg_max_chunk=4, agg_smem_kb=96)
+VARIANTS = [("ldg_v2", dict(agg_kernel=1, agg_max_vec=2)), ("ldg_v4", dict(agg_kernel=1, agg_max_vec=4)),
+            ("bulk", dict(agg_kernel=2)), ("bulk_n4", dict(agg_kernel=2, agg_nbuf=4)),
+            ("bulk_n8", dict(agg_kernel=2, agg_nbuf=8)), ("bulk_64k", dict(agg_kernel=2, agg_smem_kb=64)),
+            ("bulk_180k", dict(agg_kernel=2, agg_smem_kb=180))]
+
+
+def run(N, F, B, K, p, n_aug, reps=15):
+    dev = torch.device("cuda")
+    X = gm.DeviceFeatures(synth.features(N, F, seed=1, device=dev))
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    # power-law-ish neighbour choice: hubs repeat (PPR top-k concentrates on hubs)
+    u = torch.rand(B * K, device=dev, generator=g)
+    col = (u.pow(2.0) * N).long().clamp_(max=N - 1).to(torch.int32).reshape(B, K)
+    val = torch.rand(B, K, device=dev, generator=g) + 0.01
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    res, ref = {}, None
+    for name, knobs in VARIANTS:
+        for k, v in {**DEFAULTS, **knobs}.items():
+            _lib.set_tuning(k, v)
+        try:
+            out = gm.aggregate_slots(X, col, val, None, p, p > 0, n_aug=n_aug, seed=7, offset=1)
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            res[name] = None
+            continue
+        if ref is None:
+            ref = out.clone()
+        else:
+            assert torch.allclose(out, ref, rtol=1e-5, atol=1e-6), f"{name} differs from the LDG kernel"
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(reps):
+            flush.zero_()                                    # flush L2 between timed launches
+            e0.record()
+            out = gm.aggregate_slots(X, col, val, None, p, p > 0, n_aug=n_aug, seed=7, offset=1)
+            e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        res[name] = ts[len(ts) // 2]
+    for k, v in DEFAULTS.items():
+        _lib.set_tuning(k, v)
+    mask = gm.dropnode_mask(B * K, n_aug, p, 7, 1, dev) if p > 0 else torch.ones((n_aug, B * K), dtype=torch.uint8, device=dev)
+    kept = int((mask.sum(0) > 0).sum())
+    nbytes = kept * F * 4 + B * K * 8 + (B + 1) * 4 + n_aug * B * F * 4
+    line = f"N={N:>8} F={F:>5} B={B:>7} K={K:>3} p={p} aug={n_aug} {nbytes/1e6:8.1f}MB |"
+    for name, t in res.items():
+        line += f" {name}:" + ("   n/a" if t is None else f"{nbytes/t/1e6:5.0f} ({100*nbytes/t/1e6/PEAK:3.0f}%)")
+    print(line, flush=True)
+
+
+if __name__ == "__main__":
+    print(f"algorithmic GB/s (pct of measured HBM peak {PEAK:.0f} GB/s); L2 flushed between launches")
+    for cfg in [(232965, 602, 16384, 32, 0.5, 2), (232965, 602, 16384, 32, 0.0, 1), (232965, 602, 131072, 32, 0.5, 2),
+                (2449029, 100, 16384, 64, 0.5, 2), (2449029, 100, 131072, 64, 0.5, 2), (2449029, 100, 131072, 64, 0.0, 1),
+                (2708, 1433, 2708, 32, 0.5, 2), (19717, 500, 19717, 16, 0.5, 2), (1000000, 64, 131072, 32, 0.5, 2),
+                (232965, 602, 250, 64, 0.5, 2)]:
+        run(*cfg)
