@@ -299,7 +299,7 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line))
+        emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -405,10 +405,27 @@ def run_reference(args):
                              "aggregate_rows_per_s": S * args.steps / sum(b for _, b in times)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_line(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit_line(line: dict) -> None:
+    """The contract is ONE JSON line on stdout; libraries (NCCL's version banner, ...) write to fd 1
+    too, so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
