@@ -267,14 +267,15 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
                 __syncthreads();
                 if (tid == 0) st_edges += total;
-                for (unsigned e0 = (unsigned)(tid >> 5) * (32u * kEdgeUnroll); e0 < total;
-                     e0 += (BLOCK / 32) * (32u * kEdgeUnroll)) {
+                // edge e of the tile goes to thread e % BLOCK: every warp gets work as soon as the tile has
+                // BLOCK edges, and a warp's 32 lanes read 32 consecutive `indices` entries
+                for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += BLOCK * kEdgeUnroll) {
                     int v[kEdgeUnroll];
                     double add[kEdgeUnroll];
                     bool ok[kEdgeUnroll];
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++) {
-                        const unsigned e = e0 + q * 32u + lane;
+                        const unsigned e = e0 + q * BLOCK + lane;
                         ok[q] = e < total;
                         v[q] = src; add[q] = 0.0;
                         if (ok[q]) {
