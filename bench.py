@@ -131,7 +131,8 @@ def build_workload(name, device):
         indptr = torch.from_numpy(z["indptr"]).to(device)
         indices = torch.from_numpy(z["indices"]).to(device)
     else:
-        indptr, indices = synth.powerlaw_csr(w["n"], w["draws"], seed=0, device=device)
+        indptr, indices = synth.powerlaw_csr(w["n"], w["draws"], seed=0, device=device,
+                                             relabel=os.environ.get("GP_BENCH_NO_RELABEL") is None)
     n = int(indptr.numel() - 1)
     return indptr, indices, n
 
@@ -244,7 +245,10 @@ def run_ours(args):
                  "traffic": load_traffic(args.workload, "gfpush_kernel"), "peak_source": peak_src,
                  "ms_per_launch": t_push / args.steps * 1e3, "share_of_step": t_push / t_dev,
                  "edges_per_s": stats["edges_pushed"] / t_push, "edges_per_source": stats["edges_pushed"] / (S * args.steps),
-                 "algorithmic_bytes_per_launch": push_bytes / args.steps}
+                 "algorithmic_bytes_per_launch": push_bytes / args.steps,
+                 "hash_tier_sources": stats.get("hash_sources"), "hash_tier_fallbacks": stats.get("hash_fallbacks"),
+                 "frontier_per_source": stats["frontier_total"] / (S * args.steps),
+                 "support_per_source": stats["support_total"] / (S * args.steps)}
     roof_agg = {"kernel": "aggregate_fwd_kernel", "bound": "hbm", "achieved": agg_bytes / t_agg / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": agg_bytes / t_agg / 1e9 / peak,
                 "traffic": load_traffic(args.workload, "aggregate_fwd_kernel"), "peak_source": peak_src,

@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <string>
 
+extern int g_push_hash_slots;  // gfpush.cu
+
 namespace {
 
 constexpr int kAggBlock = 256;  // 8 warps per CTA
@@ -733,6 +735,10 @@ int gp_set_tuning(const char *key, int64_t value) {
     else if (k == "agg_max_vec") g_agg_max_vec = (int)value;
     else if (k == "agg_max_chunk") g_agg_max_chunk = (int)value;
     else if (k == "agg_smem_kb") g_agg_smem_kb = (int)value;
+    else if (k == "push_hash_slots") {
+        GP_REQUIRE(value == 0 || (value >= 1024 && (value & (value - 1)) == 0), "push_hash_slots must be 0 or a power of two >= 1024");
+        g_push_hash_slots = (int)value;
+    }
     else { gp_set_error("unknown tuning key '%s'", key); return GP_ERR_INVALID; }
     return GP_OK;
 }

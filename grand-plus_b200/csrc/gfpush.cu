@@ -29,6 +29,9 @@
 #include <new>
 #include <vector>
 
+// tuning knob (gp_set_tuning "push_hash_slots"): slots of the L2-resident hash tier, 0 disables it
+int g_push_hash_slots = 32768;
+
 namespace {
 
 constexpr int kHistBins = 2048;     // 11-bit radix digits
@@ -69,12 +72,18 @@ struct PushParams {
     int *push_deg;     // [ctas][capF]
     double *push_val;  // [ctas][capF]  r/deg
     int *nxt_id;       // [ctas][capF]  ids of the next frontier (first-touch order)
+    Slot *htab;        // HBM mode, optional: [ctas][hash_slots] open-addressed {next residue, key, support position};
+                       // small enough (512 KB per CTA) to stay L2-resident across sources
+    int hash_slots;    // power of two, 0 = tier disabled
+    int hash_shift;    // 32 - log2(hash_slots)
+    int hash_limit;    // abort to the direct-addressed table when the support outgrows this
+    int *sup_slot;     // [ctas][capS]  hash slot of each support entry (for the per-source wipe)
     int *sup_id;       // [ctas][capS]  reserve support: node ids ...
     double *sup_val;   // [ctas][capS]  ... and reserve values, compact (first-touch order)
     long long capF, capS;
     unsigned long long *queue;  // [1] next source
     unsigned long long *stats;  // [0] edges [1] frontier [2] support [3] error flags
-    unsigned long long *cum;    // [0] edges [1] frontier [2] support [3] sources; never reset by a call
+    unsigned long long *cum;    // [0] edges [1] frontier [2] support [3] sources [4] hash-tier sources [5] fallbacks
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -90,6 +99,7 @@ struct PushSmem {
     int bid[kBucketCap];
     long long it;
     int n_push, n_nxt, n_sup, n_out, n_bucket;
+    int abort, h_tries, h_fails, use_hash;
     int sel_bin, sel_above, sel_inbin;
 };
 
@@ -162,37 +172,65 @@ __device__ __forceinline__ void emit(const PushParams &P, long long it, int src,
     if (P.out_val32) P.out_val32[o] = (float)v;
 }
 
-// Per-CTA view of the next-residue table.
+constexpr int kEmptyKey = -1;
+constexpr int kMaxProbe = 48;
+
+// Per-CTA view of the next-residue table.  Three tiers:
+//   SMEM  dense double[n] in shared memory (graphs up to ~25 K nodes);
+//   HASH  open-addressed 16-byte slots, 512 KB per CTA: all 148 tables together stay L2-resident, so a
+//         source costs no DRAM traffic for its table; a source whose support outgrows it restarts on
+//   SLAB  the direct-addressed Slot[n] table in HBM (epoch-tagged, never reset).
+// A "handle" is what the next-frontier list stores: the node id (SMEM, SLAB) or the slot index (HASH).
 template <bool SMEM_NXT>
 struct Tables {
-    Slot *tab;      // HBM mode
-    int2 *meta;     // SMEM mode
-    double *s_nxt;  // SMEM mode
-    // next[v] += x; true when v had no residue yet (first touch at this level)
-    __device__ __forceinline__ bool add_next(int v, double x) const {
-        double *p = SMEM_NXT ? (s_nxt + v) : &tab[v].nxt;
-        return atomicAdd(p, x) == 0.0;  // graph.h:98
+    Slot *tab;      // SLAB
+    int2 *meta;     // SMEM
+    double *s_nxt;  // SMEM
+    Slot *htab;     // HASH
+    unsigned hmask;
+    int hshift;
+    bool use_hash;
+
+    // next[v] += x.  Returns true on the first touch at this level.  In HASH mode `claimed` says the
+    // node was inserted by this call (it is new to the source's support) and `overflow` that no slot
+    // was found within kMaxProbe probes (the update is dropped; the source will be restarted).
+    __device__ __forceinline__ bool add_next(int v, double x, int &handle, bool &claimed, bool &overflow) const {
+        claimed = false; overflow = false;
+        if (SMEM_NXT) { handle = v; return atomicAdd(s_nxt + v, x) == 0.0; }
+        if (!use_hash) { handle = v; return atomicAdd(&tab[v].nxt, x) == 0.0; }  // graph.h:98
+        unsigned h = ((unsigned)v * 2654435761u) >> hshift;
+        for (int probe = 0; probe < kMaxProbe; probe++, h = (h + 1) & hmask) {
+            int k = __ldcg(&htab[h].epoch);  // the key lives in the epoch field
+            if (k == kEmptyKey) {
+                k = atomicCAS(&htab[h].epoch, kEmptyKey, v);
+                if (k == kEmptyKey) { claimed = true; k = v; }
+            }
+            if (k == v) { handle = (int)h; return atomicAdd(&htab[h].nxt, x) == 0.0; }
+        }
+        overflow = true; handle = 0;
+        return false;
     }
-    // Takes next[v] (leaving 0).  pos >= 0: v already has a reserve entry at that position.
-    __device__ __forceinline__ double take(int v, int epoch, int &pos) const {
+    // Takes next[handle] (the caller clears it with put).  pos >= 0: the node already has a reserve entry.
+    __device__ __forceinline__ double take(int handle, int epoch, int &pos, int &v) const {
         if (SMEM_NXT) {
+            v = handle;
             const double x = s_nxt[v];
             s_nxt[v] = 0.0;
             const int2 m = meta[v];
             pos = (m.x == epoch) ? m.y : -1;
             return x;
-        } else {
-            const double4 *unused = nullptr; (void)unused;
-            // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
-            const int4 raw = __ldcg(reinterpret_cast<const int4 *>(tab + v));
-            pos = (raw.z == epoch) ? raw.w : -1;
-            return __hiloint2double(raw.y, raw.x);
         }
+        // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
+        const int4 raw = __ldcg(reinterpret_cast<const int4 *>((use_hash ? htab : tab) + handle));
+        if (use_hash) { v = raw.z; pos = raw.w; }
+        else { v = handle; pos = (raw.z == epoch) ? raw.w : -1; }
+        return __hiloint2double(raw.y, raw.x);
     }
-    // Clears next[v] and records (epoch, pos): one 16-byte write (HBM) / 8-byte write (SMEM).
-    __device__ __forceinline__ void put(int v, int epoch, int pos, bool changed) const {
-        if (SMEM_NXT) { if (changed) meta[v] = make_int2(epoch, pos); }
-        else *reinterpret_cast<int4 *>(tab + v) = make_int4(0, 0, epoch, pos);
+    // Clears next[handle]; SLAB/SMEM also record (epoch, pos).
+    __device__ __forceinline__ void put(int handle, int epoch, int pos, bool changed) const {
+        if (SMEM_NXT) { if (changed) meta[handle] = make_int2(epoch, pos); }
+        else if (use_hash) htab[handle].nxt = 0.0;
+        else *reinterpret_cast<int4 *>(tab + handle) = make_int4(0, 0, epoch, pos);
     }
 };
 
@@ -208,6 +246,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     T.tab = SMEM_NXT ? nullptr : P.tab + cta * (long long)P.n;
     T.meta = SMEM_NXT ? P.meta + cta * (long long)P.n : nullptr;
     T.s_nxt = s_nxt_dyn;
+    T.htab = (SMEM_NXT || P.hash_slots == 0) ? nullptr : P.htab + cta * (long long)P.hash_slots;
+    T.hmask = (unsigned)(P.hash_slots - 1);
+    T.hshift = P.hash_shift;
+    T.use_hash = false;
+    int *sup_slot = P.sup_slot + cta * P.capS;
     int *push_start = P.push_start + cta * P.capF;
     int *push_deg = P.push_deg + cta * P.capF;
     double *push_val = P.push_val + cta * P.capF;
@@ -220,16 +263,26 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         for (int i = tid; i < P.n; i += BLOCK) s_nxt_dyn[i] = 0.0;
     }
     unsigned long long st_edges = 0, st_frontier = 0, st_support = 0, st_sources = 0;  // thread 0 only
+    unsigned long long st_hash = 0, st_fallback = 0;
+    unsigned long long att_edges = 0, att_frontier = 0;  // work of the current attempt; committed when it completes
+    if (tid == 0) { sm.h_tries = 0; sm.h_fails = 0; }
+    bool retry_on_slab = false;
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            sm.it = (long long)atomicAdd(P.queue, 1ull);
-            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0;
+            if (!retry_on_slab) sm.it = (long long)atomicAdd(P.queue, 1ull);
+            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0; sm.abort = 0;
+            // tier choice: the hash tier unless this is a restart or it keeps overflowing on this CTA
+            sm.use_hash = !SMEM_NXT && P.hash_slots > 0 && !retry_on_slab &&
+                          !(sm.h_tries >= 4 && 2 * sm.h_fails > sm.h_tries);
+            att_edges = 0; att_frontier = 0;
         }
         __syncthreads();
         const long long it = sm.it;
         if (it >= P.S) break;
+        T.use_hash = sm.use_hash != 0;
+        retry_on_slab = false;
         const int src = P.node_idx[it];
         if (src < 0 || src >= P.n) {  // refuse instead of reading out of bounds
             if (tid == 0) atomicOr(err, kErrBadSource);
@@ -239,8 +292,15 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         const int epoch = P.epoch_base + (int)it + 1;
         // level 0: residue = {src: 1}, reserve = {src: 0} (graph.h:80-81); settle it right away
         if (tid == 0) {
-            st_sources++; st_frontier++;
-            T.put(src, epoch, 0, true);
+            att_frontier++;
+            if (T.use_hash) {
+                sm.h_tries++;
+                bool claimed, overflow; int h;
+                T.add_next(src, 0.0, h, claimed, overflow);   // the table is empty: claims its home slot
+                T.htab[h].pos = 0; sup_slot[0] = h;
+            } else {
+                T.put(src, epoch, 0, true);
+            }
             sup_id[0] = src; sup_val[0] = P.coef[0]; sm.n_sup = 1;
             if (P.L > 1) {
                 const int a = P.indptr[src], b = P.indptr[src + 1];
@@ -266,7 +326,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
                 __syncthreads();
-                if (tid == 0) st_edges += total;
+                if (tid == 0) att_edges += total;
                 // edge e of the tile goes to thread e % BLOCK: every warp gets work as soon as the tile has
                 // BLOCK edges, and a warp's 32 lanes read 32 consecutive `indices` entries
                 for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += BLOCK * kEdgeUnroll) {
@@ -285,18 +345,32 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                             if (st >= 0) v[q] = __ldg(P.indices + st + (e - sm.off[t]));  // graph.h:96-97
                         }
                     }
-                    bool fresh[kEdgeUnroll];
+                    bool fresh[kEdgeUnroll], claimed[kEdgeUnroll];
+                    int handle[kEdgeUnroll];
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next(v[q], add[q]);
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        fresh[q] = false; claimed[q] = false; handle[q] = 0;
+                        bool overflow = false;
+                        if (ok[q]) fresh[q] = T.add_next(v[q], add[q], handle[q], claimed[q], overflow);
+                        if (overflow) sm.abort = 1;
+                    }
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         const long long pos = warp_append_pos(fresh[q], P.capF, &sm.n_nxt, err);
-                        if (pos >= 0) nxt_id[pos] = v[q];
+                        if (pos >= 0) nxt_id[pos] = handle[q];
+                        if (T.use_hash) {  // a node new to this source: give it its reserve entry now
+                            const long long ps = warp_append_pos(claimed[q], P.capS, &sm.n_sup, err);
+                            if (ps >= 0) {
+                                sup_id[ps] = v[q]; sup_slot[ps] = handle[q]; sup_val[ps] = 0.0;
+                                T.htab[handle[q]].pos = (int)ps;
+                            }
+                        }
                     }
                 }
                 __syncthreads();
             }
             if (n_push == 0) __syncthreads();
+            if (T.use_hash && (sm.abort || sm.n_sup > P.hash_limit)) break;  // CTA-uniform: restart on the slab
             // ---------------------------------------------------------------- settle (graph.h:85-93,102)
             // Every node of the new frontier, independently: take its residue, credit the reserve,
             // and decide now whether it will push at the next level.
@@ -304,7 +378,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const int next_level = level + 1;
             const bool will_push = next_level < P.L - 1;
             const double c = P.coef[next_level];
-            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
+            if (tid == 0) { att_frontier += n_nxt; sm.n_push = 0; }
             __syncthreads();
             for (int base = 0; base < n_nxt; base += BLOCK * kSettleUnroll) {
                 int v[kSettleUnroll];
@@ -317,11 +391,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     v[q] = ok[q] ? nxt_id[j] : 0;
                 }
                 double x[kSettleUnroll];
-                int pos[kSettleUnroll];
+                int pos[kSettleUnroll], hnd[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    pos[q] = 0; x[q] = 0.0;
-                    if (ok[q]) x[q] = T.take(v[q], epoch, pos[q]);
+                    pos[q] = 0; x[q] = 0.0; hnd[q] = v[q];
+                    if (ok[q]) x[q] = T.take(hnd[q], epoch, pos[q], v[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
@@ -335,10 +409,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     const long long ps = warp_append_pos(first, P.capS, &sm.n_sup, err);
                     if (first) {
                         if (ps >= 0) { sup_id[ps] = v[q]; sup_val[ps] = c * x[q]; }
-                        T.put(v[q], epoch, (int)max(ps, 0ll), true);
+                        T.put(hnd[q], epoch, (int)max(ps, 0ll), true);
                     } else if (ok[q]) {
                         sup_val[pos[q]] += c * x[q];
-                        T.put(v[q], epoch, pos[q], false);
+                        T.put(hnd[q], epoch, pos[q], false);
                     }
                     bool push = false;
                     int st = -1, dg = 1;
@@ -358,11 +432,24 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             if (tid == 0) sm.n_nxt = 0;
             __syncthreads();
         }
+        const int n_sup = min((long long)sm.n_sup, P.capS);
+        if (T.use_hash) {
+            // wipe this source's entries (keys back to empty, residues to 0): the table is L2-resident
+            const bool aborted = sm.abort || sm.n_sup > P.hash_limit;
+            for (int j = tid; j < n_sup; j += BLOCK)
+                *reinterpret_cast<int4 *>(T.htab + sup_slot[j]) = make_int4(0, 0, kEmptyKey, 0);
+            if (aborted) {
+                if (tid == 0) { sm.h_fails++; st_fallback++; }
+                retry_on_slab = true;   // same source again, on the direct-addressed table
+                continue;
+            }
+            if (tid == 0) st_hash++;
+        }
+        if (tid == 0) { st_sources++; st_edges += att_edges; st_frontier += att_frontier; }
         for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
         __syncthreads();
 
         // ------------------------------------------------------------------ top-k, graph.h:111-126
-        const int n_sup = min((long long)sm.n_sup, P.capS);
         if (tid == 0) st_support += n_sup;
         // pass 0: exponent histogram of the compact reserve values (coalesced; no table access)
         for (int j = tid; j < n_sup; j += BLOCK) {
@@ -443,16 +530,20 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         atomicAdd(P.cum + 1, st_frontier);
         atomicAdd(P.cum + 2, st_support);
         atomicAdd(P.cum + 3, st_sources);
+        atomicAdd(P.cum + 4, st_hash);
+        atomicAdd(P.cum + 5, st_fallback);
     }
 }
 
 // Table invariant between sources: next residue 0; epoch 0 never matches a source (epochs start at 1).
-__global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots) {
+__global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots, int4 *htab, long long n_hslots) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
         if (tab16) tab16[i] = make_int4(0, 0, 0, 0);
         else meta8[i] = make_int2(0, 0);
     }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_hslots; i += stride)
+        htab[i] = make_int4(0, 0, kEmptyKey, 0);
 }
 
 // CSR sanity: indptr[0]==0, non-decreasing, indptr[n]==nnz, 0 <= indices < n.
@@ -486,6 +577,7 @@ struct gp_graph {
     size_t scratch_bytes = 0;
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
+    int scratch_hash_slots = 0;
     long long epoch_base = 0;              // sources pushed since the tables were last initialised
     double *d_coef = nullptr;              // [kMaxLevels]
     unsigned long long *d_ctrl = nullptr;  // [0] queue, [1..4] stats, [8..11] cumulative counters
@@ -521,7 +613,8 @@ struct Plan {
     long long ctas, capF, capS;
     size_t dyn_smem;
     size_t bytes;
-    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand;
+    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand, off_htab, off_sup_slot;
+    int hash_slots;
 };
 
 int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
@@ -559,6 +652,14 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         per_sm = std::min(per_sm, fit);
     }
     long long ctas = (long long)g->num_sms * per_sm;  // scratch is sized for a full grid; small calls launch fewer
+    // Hash tier (HBM mode): 32 K slots = 512 KB per CTA, 76 MB for 148 CTAs -- inside the 126 MB L2 next to the
+    // compact per-CTA lists.  Pointless when even the bound on one level's frontier cannot fit.
+    int hash_slots = 0;
+    if (mode == GP_SCRATCH_HBM && g_push_hash_slots > 0 && n > g_push_hash_slots) {
+        hash_slots = g_push_hash_slots;
+        // when capS is a true bound on the support, a table of 1.6 x capS never overflows
+        while (hash_slots > 1024 && (long long)(hash_slots / 2) * 5 / 8 > capS) hash_slots /= 2;
+    }
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
         p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 8), 256);
@@ -568,6 +669,8 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         p->off_nxt_id = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_sup_id = o; o += align_up((size_t)c * capS * 4, 256);
         p->off_cand = o; o += align_up((size_t)c * capS * 8, 256);
+        p->off_htab = o; o += align_up((size_t)c * hash_slots * 16, 256);
+        p->off_sup_slot = o; o += align_up((size_t)c * (hash_slots ? capS : 0) * 4, 256);
         return o;
     };
     size_t budget = (size_t)g->cfg.max_scratch_bytes;
@@ -578,7 +681,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     }
     Plan tmp{};
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
-    pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
+    pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS; pl->hash_slots = hash_slots;
     pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : 0;
     pl->bytes = bytes_for(ctas, pl);
     GP_REQUIRE(pl->bytes <= budget || ctas == 1, "scratch does not fit the budget");
@@ -588,6 +691,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
 int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream) {
     const bool same = g->scratch && g->scratch_bytes >= pl.bytes && g->scratch_ctas == pl.ctas &&
                       g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode &&
+                      g->scratch_hash_slots == pl.hash_slots &&
                       g->epoch_base + S < (1ll << 31) - 2;  // epoch tags are int32: re-initialise before they wrap
     if (same) return GP_OK;
     if (g->scratch && g->scratch_bytes < pl.bytes) {
@@ -603,10 +707,12 @@ int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream
     char *base = (char *)g->scratch;
     init_tables_kernel<<<g->num_sms * 8, 256, 0, stream>>>(
         pl.mode == GP_SCRATCH_HBM ? (int4 *)(base + pl.off_tab) : nullptr,
-        pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n);
+        pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n,
+        (int4 *)(base + pl.off_htab), pl.ctas * (long long)pl.hash_slots);
     GP_CUDA_TRY(cudaGetLastError());
     g->epoch_base = 0;
     g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
+    g->scratch_hash_slots = pl.hash_slots;
     return GP_OK;
 }
 
@@ -656,6 +762,12 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.nxt_id = (int *)(base + pl.off_nxt_id);
     P.sup_id = (int *)(base + pl.off_sup_id);
     P.sup_val = (double *)(base + pl.off_cand);
+    P.htab = (Slot *)(base + pl.off_htab);
+    P.sup_slot = (int *)(base + pl.off_sup_slot);
+    P.hash_slots = pl.hash_slots;
+    P.hash_shift = 32;
+    for (int h = pl.hash_slots; h > 1; h >>= 1) P.hash_shift--;
+    P.hash_limit = (int)std::min<long long>((long long)pl.hash_slots * 5 / 8, pl.capS - 1);
     P.capF = pl.capF; P.capS = pl.capS;
     P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 8;
     rc = pl.block == 256 ? launch_push<256>(P, pl, stream)
@@ -822,12 +934,13 @@ int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset) {
     std::lock_guard<std::mutex> lk(g->mu);
     DeviceGuard guard(g->device);
     GP_CUDA_TRY(cudaDeviceSynchronize());
-    unsigned long long h[4];
+    unsigned long long h[6];
     GP_CUDA_TRY(cudaMemcpy(h, g->d_ctrl + 8, sizeof h, cudaMemcpyDeviceToHost));
     if (reset) GP_CUDA_TRY(cudaMemset(g->d_ctrl + 8, 0, sizeof h));
     *out = g->last;
     out->edges_pushed = (int64_t)h[0]; out->frontier_total = (int64_t)h[1];
     out->support_total = (int64_t)h[2]; out->sources = (int64_t)h[3];
+    out->hash_sources = (int64_t)h[4]; out->hash_fallbacks = (int64_t)h[5];
     return GP_OK;
 }
 

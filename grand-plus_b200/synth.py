@@ -45,7 +45,8 @@ def uniform01(n: int, seed: int, stream: int, device) -> torch.Tensor:
     return _lsr(h, 11).to(torch.float64) * (1.0 / (1 << 53))
 
 
-def powerlaw_csr(n: int, n_draws: int, gamma: float = 2.5, seed: int = 0, device="cpu", chunk: int = 1 << 26):
+def powerlaw_csr(n: int, n_draws: int, gamma: float = 2.5, seed: int = 0, device="cpu", chunk: int = 1 << 26,
+                 relabel: bool = True):
     """Chung-Lu graph: weights w_i = (i+1)^(-1/(gamma-1)), `n_draws` endpoint pairs by inverse CDF,
     random relabelling, self pairs dropped, symmetrised, de-duplicated, + I, sorted.
     Returns (indptr int32 [n+1], indices int32 [nnz]) torch tensors on `device`."""
@@ -55,6 +56,8 @@ def powerlaw_csr(n: int, n_draws: int, gamma: float = 2.5, seed: int = 0, device
     cdf /= cdf[-1].clone()
     del w
     perm = torch.argsort(splitmix64(torch.arange(n, dtype=torch.int64, device=dev) + _s64(seed * 77 + 12345)))
+    if not relabel:  # ids stay sorted by expected degree (locality experiment)
+        perm = torch.arange(n, dtype=torch.int64, device=dev)
     keys = []
     for lo in range(0, n_draws, chunk):
         m = min(chunk, n_draws - lo)

@@ -105,6 +105,8 @@ typedef struct {
     int64_t scratch_bytes;   /* device scratch held by the handle                     */
     int32_t scratch_mode;    /* mode actually used (gp_scratch_mode)                  */
     int32_t kernel_launches; /* kernels launched by the call                          */
+    int64_t hash_sources;    /* cumulative stats only: sources finished on the L2-resident hash tier  */
+    int64_t hash_fallbacks;  /* cumulative stats only: sources restarted on the direct-addressed table */
 } gp_push_stats;
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out);
 /* Counters summed over every gfpush since creation / the last reset (device-wide synchronise);
@@ -188,7 +190,8 @@ int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, 
 
 /* Performance knobs for sweeps (profiles/); defaults are the measured best.  Keys: "agg_kernel"
  * (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf", "agg_max_vec",
- * "agg_max_chunk", "agg_smem_kb".  Results never depend on them. */
+ * "agg_max_chunk", "agg_smem_kb", "push_hash_slots" (slots of GFPush's L2-resident hash tier, 0 = off).
+ * Results never depend on them. */
 int gp_set_tuning(const char *key, int64_t value);
 
 #ifdef __cplusplus

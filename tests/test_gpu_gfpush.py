@@ -197,3 +197,43 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
             assert abs(gv.min() - rv.min()) <= 1e-9 * rv.min()   # differs only by a tie at the cut
     assert worst < 1e-11
     assert same > 0.8 * n
+
+
+@pytest.mark.parametrize("slots", [0, 1024, 32768])
+def test_gfpush_hash_tier_on_off_and_fallback(slots):
+    """The L2-resident hash tier, the direct-addressed table, and the restart from one to the other
+    (a 1024-slot table overflows for most sources) must all give the oracle's rows and work counters."""
+    from grandplus_b200 import _lib, synth
+    indptr, indices = synth.powerlaw_csr(60_000, 700_000, seed=5)
+    indptr, indices = indptr.numpy(), indices.numpy()
+    src = synth.sources(60_000, 300, seed=4).numpy()
+    coef = og.coef_for("ppr", 6, 0.05)
+    _lib.set_tuning("push_hash_slots", slots)
+    try:
+        g = _graph(indptr, indices, scratch_mode=HBM)
+        g.cumulative_stats(reset=True)
+        row, col, val = _run(g, src, coef, 1e-5, 32)
+        st = g.cumulative_stats()
+    finally:
+        _lib.set_tuning("push_hash_slots", 32768)
+    worst = check_topk_rows(indptr, indices, src, coef, 1e-5, 32, col, val, row=row, max_rows=100)
+    assert worst < 1e-11
+    _, _, _, ost = og.gfpush(indptr, indices, src, coef, 1e-5, 32)
+    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * ost.edges_pushed      # restarted work is not double counted
+    assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
+    assert st["sources"] == len(src)
+    if slots == 0:
+        assert st["hash_sources"] == 0 and st["hash_fallbacks"] == 0
+    elif slots == 1024:
+        assert st["hash_fallbacks"] > 0
+    else:
+        assert st["hash_sources"] > 0.5 * len(src)
+    # the tables must be clean afterwards: a second run on the same handle gives the same rows
+    _lib.set_tuning("push_hash_slots", slots)
+    try:
+        row2, col2, val2 = _run(g, src, coef, 1e-5, 32)
+    finally:
+        _lib.set_tuning("push_hash_slots", 32768)
+    for (ac, av), (bc, bv) in zip(og.rows_as_sets(col, val, 32), og.rows_as_sets(col2, val2, 32)):
+        if np.array_equal(ac, bc):
+            np.testing.assert_allclose(av, bv, rtol=1e-12)
