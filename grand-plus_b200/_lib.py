@@ -81,6 +81,7 @@ SIGNATURES = {
                                  c_vp, c_vp, c_vp]),
     "gp_gfpush_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32, ctypes.c_double,
                                         ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "gp_gfpush_phase_cycles": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64 * 8), ctypes.c_int]),
     "gp_gfpush_last_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(PushStats)]),
     "gp_gfpush_cumulative_stats": (ctypes.c_int, [c_vp, ctypes.POINTER(PushStats), ctypes.c_int]),
     "gp_aggregate_fwd": (ctypes.c_int, [ctypes.POINTER(AggregateArgs), c_vp]),
@@ -118,6 +119,11 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if lib.gp_abi_version() != 1:
         raise ImportError(f"{LIB_NAME} has ABI version {lib.gp_abi_version()}, this binding expects 1")
     _lib = lib
+    # GP_TUNING="key=value,key=value": performance knobs for sweeps (gp_set_tuning; results never depend on them)
+    for item in filter(None, os.environ.get("GP_TUNING", "").split(",")):
+        k, v = item.split("=")
+        if lib.gp_set_tuning(k.strip().encode(), int(v)) != GP_OK:
+            raise GPError(-1, lib.gp_last_error().decode("utf-8", "replace"))
     return lib
 
 

@@ -23,14 +23,25 @@
 //   Residues stay fp64 end to end (the threshold test r >= rmax*deg is a hard comparison).
 #include "gp_common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <mutex>
 #include <new>
 #include <vector>
 
-// tuning knob (gp_set_tuning "push_hash_slots"): slots of the L2-resident hash tier, 0 disables it
-int g_push_hash_slots = 32768;
+// tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
+int g_push_hash = 1;          // "push_hash": 0 = direct-addressed slabs only
+int g_push_cluster = 0;       // "push_cluster": CTAs per source (1,2,4,8,16), 0 = from the pilot statistics
+int g_push_hash_slots = 0;    // "push_hash_slots": table capacity per cluster, 0 = from the pilot statistics
+int g_push_l2_mb = 48;        // "push_l2_mb": L2 budget the live tables should fit
+int g_push_load_pct = 60;     // "push_load_pct": (support bound)/(table size) the per-level sizing aims at
+int g_push_list_div = 8;      // "push_list_div": levels with fewer than C/list_div edges settle via the first-touch list
+int g_push_hash_block = 1024; // "push_hash_block": threads per CTA of the hash tier (512 or 1024)
+int g_push_max_clusters = 0;  // "push_max_clusters": cap on concurrently processed sources of the hash tier (0 = all SMs)
+int g_push_pilot = 256;       // "push_pilot": sources pushed on the slabs to measure the support before choosing G
+int g_push_tuning_gen = 0;    // bumped by gp_set_tuning so that handles re-plan
 
 namespace {
 
@@ -72,18 +83,16 @@ struct PushParams {
     int *push_deg;     // [ctas][capF]
     double *push_val;  // [ctas][capF]  r/deg
     int *nxt_id;       // [ctas][capF]  ids of the next frontier (first-touch order)
-    Slot *htab;        // HBM mode, optional: [ctas][hash_slots] open-addressed {next residue, key, support position};
-                       // small enough (512 KB per CTA) to stay L2-resident across sources
-    int hash_slots;    // power of two, 0 = tier disabled
-    int hash_shift;    // 32 - log2(hash_slots)
-    int hash_limit;    // abort to the direct-addressed table when the support outgrows this
-    int *sup_slot;     // [ctas][capS]  hash slot of each support entry (for the per-source wipe)
     int *sup_id;       // [ctas][capS]  reserve support: node ids ...
     double *sup_val;   // [ctas][capS]  ... and reserve values, compact (first-touch order)
     long long capF, capS;
     unsigned long long *queue;  // [1] next source
     unsigned long long *stats;  // [0] edges [1] frontier [2] support [3] error flags
-    unsigned long long *cum;    // [0] edges [1] frontier [2] support [3] sources [4] hash-tier sources [5] fallbacks
+    unsigned long long *cum;    // [0] edges [1] frontier [2] support [3] sources; never reset by a call
+    // redo mode (second pass after gfpush_hash_kernel): the queue indexes redo[0 .. *redo_count)
+    const int *redo;
+    const unsigned long long *redo_count;
+    unsigned long long *max_support;  // largest reserve support of any source of this launch (pilot statistics)
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -99,7 +108,6 @@ struct PushSmem {
     int bid[kBucketCap];
     long long it;
     int n_push, n_nxt, n_sup, n_out, n_bucket;
-    int abort, h_tries, h_fails, use_hash;
     int sel_bin, sel_above, sel_inbin;
 };
 
@@ -133,9 +141,11 @@ __device__ __forceinline__ int owner_of_edge(const unsigned *off, unsigned e) {
 }
 
 // Finds the radix bin holding the kk-th largest among `hist` (bins ordered ascending by key).
-// Results in sm.sel_bin / sel_above (count in strictly higher bins) / sel_inbin; returns total.
+// Results in *sel_bin / *sel_above (count in strictly higher bins) / *sel_inbin; returns total.
+// Every thread of the CTA must call it (block scan inside).
 template <int BLOCK>
-__device__ __forceinline__ unsigned select_bin(PushSmem<BLOCK> &sm, int nbins, int kk, bool kk_is_cap) {
+__device__ __forceinline__ unsigned select_bin_generic(const unsigned *hist, unsigned *warp_scan, int nbins, int kk,
+                                                       bool kk_is_cap, int *sel_bin, int *sel_above, int *sel_inbin) {
     // thread t owns bins [hi - per + 1, hi], hi = nbins-1 - t*per, walking from the top
     const int per = (nbins + BLOCK - 1) / BLOCK;
     const int tid = threadIdx.x;
@@ -144,27 +154,32 @@ __device__ __forceinline__ unsigned select_bin(PushSmem<BLOCK> &sm, int nbins, i
 #pragma unroll 4
     for (int i = 0; i < per; i++) {
         int b = hi - i;
-        if (b >= 0) local += sm.hist[b];
+        if (b >= 0) local += hist[b];
     }
     unsigned total;
-    unsigned above = gp_block_exclusive_scan<BLOCK>(local, sm.warp_scan, total);
+    unsigned above = gp_block_exclusive_scan<BLOCK>(local, warp_scan, total);
     unsigned want = kk_is_cap ? min((unsigned)kk, total) : (unsigned)kk;
     if (want > 0 && above < want && want <= above + local) {
         unsigned acc = above;
         for (int i = 0; i < per; i++) {
             int b = hi - i;
             if (b < 0) break;
-            unsigned h = sm.hist[b];
-            if (acc + h >= want) { sm.sel_bin = b; sm.sel_above = (int)acc; sm.sel_inbin = (int)h; break; }
+            unsigned h = hist[b];
+            if (acc + h >= want) { *sel_bin = b; *sel_above = (int)acc; *sel_inbin = (int)h; break; }
             acc += h;
         }
     }
-    if (want == 0 && tid == 0) { sm.sel_bin = -1; sm.sel_above = 0; sm.sel_inbin = 0; }
+    if (want == 0 && tid == 0) { *sel_bin = -1; *sel_above = 0; *sel_inbin = 0; }
     __syncthreads();
     return total;
 }
+template <int BLOCK>
+__device__ __forceinline__ unsigned select_bin(PushSmem<BLOCK> &sm, int nbins, int kk, bool kk_is_cap) {
+    return select_bin_generic<BLOCK>(sm.hist, sm.warp_scan, nbins, kk, kk_is_cap, &sm.sel_bin, &sm.sel_above, &sm.sel_inbin);
+}
 
-__device__ __forceinline__ void emit(const PushParams &P, long long it, int src, int slot, int col, double v) {
+template <class Params>
+__device__ __forceinline__ void emit(const Params &P, long long it, int src, int slot, int col, double v) {
     long long o = it * P.K + slot;
     P.out_row[o] = src;
     P.out_col[o] = col;
@@ -172,65 +187,37 @@ __device__ __forceinline__ void emit(const PushParams &P, long long it, int src,
     if (P.out_val32) P.out_val32[o] = (float)v;
 }
 
-constexpr int kEmptyKey = -1;
-constexpr int kMaxProbe = 48;
-
-// Per-CTA view of the next-residue table.  Three tiers:
-//   SMEM  dense double[n] in shared memory (graphs up to ~25 K nodes);
-//   HASH  open-addressed 16-byte slots, 512 KB per CTA: all 148 tables together stay L2-resident, so a
-//         source costs no DRAM traffic for its table; a source whose support outgrows it restarts on
-//   SLAB  the direct-addressed Slot[n] table in HBM (epoch-tagged, never reset).
-// A "handle" is what the next-frontier list stores: the node id (SMEM, SLAB) or the slot index (HASH).
+// Per-CTA view of the next-residue table.
 template <bool SMEM_NXT>
 struct Tables {
-    Slot *tab;      // SLAB
-    int2 *meta;     // SMEM
-    double *s_nxt;  // SMEM
-    Slot *htab;     // HASH
-    unsigned hmask;
-    int hshift;
-    bool use_hash;
-
-    // next[v] += x.  Returns true on the first touch at this level.  In HASH mode `claimed` says the
-    // node was inserted by this call (it is new to the source's support) and `overflow` that no slot
-    // was found within kMaxProbe probes (the update is dropped; the source will be restarted).
-    __device__ __forceinline__ bool add_next(int v, double x, int &handle, bool &claimed, bool &overflow) const {
-        claimed = false; overflow = false;
-        if (SMEM_NXT) { handle = v; return atomicAdd(s_nxt + v, x) == 0.0; }
-        if (!use_hash) { handle = v; return atomicAdd(&tab[v].nxt, x) == 0.0; }  // graph.h:98
-        unsigned h = ((unsigned)v * 2654435761u) >> hshift;
-        for (int probe = 0; probe < kMaxProbe; probe++, h = (h + 1) & hmask) {
-            int k = __ldcg(&htab[h].epoch);  // the key lives in the epoch field
-            if (k == kEmptyKey) {
-                k = atomicCAS(&htab[h].epoch, kEmptyKey, v);
-                if (k == kEmptyKey) { claimed = true; k = v; }
-            }
-            if (k == v) { handle = (int)h; return atomicAdd(&htab[h].nxt, x) == 0.0; }
-        }
-        overflow = true; handle = 0;
-        return false;
+    Slot *tab;      // HBM mode
+    int2 *meta;     // SMEM mode
+    double *s_nxt;  // SMEM mode
+    // next[v] += x; true when v had no residue yet (first touch at this level)
+    __device__ __forceinline__ bool add_next(int v, double x) const {
+        double *p = SMEM_NXT ? (s_nxt + v) : &tab[v].nxt;
+        return atomicAdd(p, x) == 0.0;  // graph.h:98
     }
-    // Takes next[handle] (the caller clears it with put).  pos >= 0: the node already has a reserve entry.
-    __device__ __forceinline__ double take(int handle, int epoch, int &pos, int &v) const {
+    // Takes next[v] (leaving 0).  pos >= 0: v already has a reserve entry at that position.
+    __device__ __forceinline__ double take(int v, int epoch, int &pos) const {
         if (SMEM_NXT) {
-            v = handle;
             const double x = s_nxt[v];
             s_nxt[v] = 0.0;
             const int2 m = meta[v];
             pos = (m.x == epoch) ? m.y : -1;
             return x;
+        } else {
+            const double4 *unused = nullptr; (void)unused;
+            // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
+            const int4 raw = __ldcg(reinterpret_cast<const int4 *>(tab + v));
+            pos = (raw.z == epoch) ? raw.w : -1;
+            return __hiloint2double(raw.y, raw.x);
         }
-        // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
-        const int4 raw = __ldcg(reinterpret_cast<const int4 *>((use_hash ? htab : tab) + handle));
-        if (use_hash) { v = raw.z; pos = raw.w; }
-        else { v = handle; pos = (raw.z == epoch) ? raw.w : -1; }
-        return __hiloint2double(raw.y, raw.x);
     }
-    // Clears next[handle]; SLAB/SMEM also record (epoch, pos).
-    __device__ __forceinline__ void put(int handle, int epoch, int pos, bool changed) const {
-        if (SMEM_NXT) { if (changed) meta[handle] = make_int2(epoch, pos); }
-        else if (use_hash) htab[handle].nxt = 0.0;
-        else *reinterpret_cast<int4 *>(tab + handle) = make_int4(0, 0, epoch, pos);
+    // Clears next[v] and records (epoch, pos): one 16-byte write (HBM) / 8-byte write (SMEM).
+    __device__ __forceinline__ void put(int v, int epoch, int pos, bool changed) const {
+        if (SMEM_NXT) { if (changed) meta[v] = make_int2(epoch, pos); }
+        else *reinterpret_cast<int4 *>(tab + v) = make_int4(0, 0, epoch, pos);
     }
 };
 
@@ -246,11 +233,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     T.tab = SMEM_NXT ? nullptr : P.tab + cta * (long long)P.n;
     T.meta = SMEM_NXT ? P.meta + cta * (long long)P.n : nullptr;
     T.s_nxt = s_nxt_dyn;
-    T.htab = (SMEM_NXT || P.hash_slots == 0) ? nullptr : P.htab + cta * (long long)P.hash_slots;
-    T.hmask = (unsigned)(P.hash_slots - 1);
-    T.hshift = P.hash_shift;
-    T.use_hash = false;
-    int *sup_slot = P.sup_slot + cta * P.capS;
     int *push_start = P.push_start + cta * P.capF;
     int *push_deg = P.push_deg + cta * P.capF;
     double *push_val = P.push_val + cta * P.capF;
@@ -262,27 +244,20 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     if (SMEM_NXT) {
         for (int i = tid; i < P.n; i += BLOCK) s_nxt_dyn[i] = 0.0;
     }
-    unsigned long long st_edges = 0, st_frontier = 0, st_support = 0, st_sources = 0;  // thread 0 only
-    unsigned long long st_hash = 0, st_fallback = 0;
-    unsigned long long att_edges = 0, att_frontier = 0;  // work of the current attempt; committed when it completes
-    if (tid == 0) { sm.h_tries = 0; sm.h_fails = 0; }
-    bool retry_on_slab = false;
+    unsigned long long st_edges = 0, st_frontier = 0, st_support = 0, st_sources = 0, st_maxsup = 0;  // thread 0 only
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
-            if (!retry_on_slab) sm.it = (long long)atomicAdd(P.queue, 1ull);
-            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0; sm.abort = 0;
-            // tier choice: the hash tier unless this is a restart or it keeps overflowing on this CTA
-            sm.use_hash = !SMEM_NXT && P.hash_slots > 0 && !retry_on_slab &&
-                          !(sm.h_tries >= 4 && 2 * sm.h_fails > sm.h_tries);
-            att_edges = 0; att_frontier = 0;
+            sm.it = (long long)atomicAdd(P.queue, 1ull);
+            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0;
         }
         __syncthreads();
-        const long long it = sm.it;
-        if (it >= P.S) break;
-        T.use_hash = sm.use_hash != 0;
-        retry_on_slab = false;
+        long long it = sm.it;
+        if (P.redo) {
+            if (it >= (long long)*P.redo_count) break;
+            it = P.redo[it];
+        } else if (it >= P.S) break;
         const int src = P.node_idx[it];
         if (src < 0 || src >= P.n) {  // refuse instead of reading out of bounds
             if (tid == 0) atomicOr(err, kErrBadSource);
@@ -292,15 +267,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         const int epoch = P.epoch_base + (int)it + 1;
         // level 0: residue = {src: 1}, reserve = {src: 0} (graph.h:80-81); settle it right away
         if (tid == 0) {
-            att_frontier++;
-            if (T.use_hash) {
-                sm.h_tries++;
-                bool claimed, overflow; int h;
-                T.add_next(src, 0.0, h, claimed, overflow);   // the table is empty: claims its home slot
-                T.htab[h].pos = 0; sup_slot[0] = h;
-            } else {
-                T.put(src, epoch, 0, true);
-            }
+            st_sources++; st_frontier++;
+            T.put(src, epoch, 0, true);
             sup_id[0] = src; sup_val[0] = P.coef[0]; sm.n_sup = 1;
             if (P.L > 1) {
                 const int a = P.indptr[src], b = P.indptr[src + 1];
@@ -326,7 +294,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
                 __syncthreads();
-                if (tid == 0) att_edges += total;
+                if (tid == 0) st_edges += total;
                 // edge e of the tile goes to thread e % BLOCK: every warp gets work as soon as the tile has
                 // BLOCK edges, and a warp's 32 lanes read 32 consecutive `indices` entries
                 for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += BLOCK * kEdgeUnroll) {
@@ -345,32 +313,18 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                             if (st >= 0) v[q] = __ldg(P.indices + st + (e - sm.off[t]));  // graph.h:96-97
                         }
                     }
-                    bool fresh[kEdgeUnroll], claimed[kEdgeUnroll];
-                    int handle[kEdgeUnroll];
+                    bool fresh[kEdgeUnroll];
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) {
-                        fresh[q] = false; claimed[q] = false; handle[q] = 0;
-                        bool overflow = false;
-                        if (ok[q]) fresh[q] = T.add_next(v[q], add[q], handle[q], claimed[q], overflow);
-                        if (overflow) sm.abort = 1;
-                    }
+                    for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next(v[q], add[q]);
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         const long long pos = warp_append_pos(fresh[q], P.capF, &sm.n_nxt, err);
-                        if (pos >= 0) nxt_id[pos] = handle[q];
-                        if (T.use_hash) {  // a node new to this source: give it its reserve entry now
-                            const long long ps = warp_append_pos(claimed[q], P.capS, &sm.n_sup, err);
-                            if (ps >= 0) {
-                                sup_id[ps] = v[q]; sup_slot[ps] = handle[q]; sup_val[ps] = 0.0;
-                                T.htab[handle[q]].pos = (int)ps;
-                            }
-                        }
+                        if (pos >= 0) nxt_id[pos] = v[q];
                     }
                 }
                 __syncthreads();
             }
             if (n_push == 0) __syncthreads();
-            if (T.use_hash && (sm.abort || sm.n_sup > P.hash_limit)) break;  // CTA-uniform: restart on the slab
             // ---------------------------------------------------------------- settle (graph.h:85-93,102)
             // Every node of the new frontier, independently: take its residue, credit the reserve,
             // and decide now whether it will push at the next level.
@@ -378,7 +332,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const int next_level = level + 1;
             const bool will_push = next_level < P.L - 1;
             const double c = P.coef[next_level];
-            if (tid == 0) { att_frontier += n_nxt; sm.n_push = 0; }
+            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
             __syncthreads();
             for (int base = 0; base < n_nxt; base += BLOCK * kSettleUnroll) {
                 int v[kSettleUnroll];
@@ -391,11 +345,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     v[q] = ok[q] ? nxt_id[j] : 0;
                 }
                 double x[kSettleUnroll];
-                int pos[kSettleUnroll], hnd[kSettleUnroll];
+                int pos[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    pos[q] = 0; x[q] = 0.0; hnd[q] = v[q];
-                    if (ok[q]) x[q] = T.take(hnd[q], epoch, pos[q], v[q]);
+                    pos[q] = 0; x[q] = 0.0;
+                    if (ok[q]) x[q] = T.take(v[q], epoch, pos[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
@@ -409,10 +363,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     const long long ps = warp_append_pos(first, P.capS, &sm.n_sup, err);
                     if (first) {
                         if (ps >= 0) { sup_id[ps] = v[q]; sup_val[ps] = c * x[q]; }
-                        T.put(hnd[q], epoch, (int)max(ps, 0ll), true);
+                        T.put(v[q], epoch, (int)max(ps, 0ll), true);
                     } else if (ok[q]) {
                         sup_val[pos[q]] += c * x[q];
-                        T.put(hnd[q], epoch, pos[q], false);
+                        T.put(v[q], epoch, pos[q], false);
                     }
                     bool push = false;
                     int st = -1, dg = 1;
@@ -432,25 +386,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             if (tid == 0) sm.n_nxt = 0;
             __syncthreads();
         }
-        const int n_sup = min((long long)sm.n_sup, P.capS);
-        if (T.use_hash) {
-            // wipe this source's entries (keys back to empty, residues to 0): the table is L2-resident
-            const bool aborted = sm.abort || sm.n_sup > P.hash_limit;
-            for (int j = tid; j < n_sup; j += BLOCK)
-                *reinterpret_cast<int4 *>(T.htab + sup_slot[j]) = make_int4(0, 0, kEmptyKey, 0);
-            if (aborted) {
-                if (tid == 0) { sm.h_fails++; st_fallback++; }
-                retry_on_slab = true;   // same source again, on the direct-addressed table
-                continue;
-            }
-            if (tid == 0) st_hash++;
-        }
-        if (tid == 0) { st_sources++; st_edges += att_edges; st_frontier += att_frontier; }
         for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
         __syncthreads();
 
         // ------------------------------------------------------------------ top-k, graph.h:111-126
-        if (tid == 0) st_support += n_sup;
+        const int n_sup = min((long long)sm.n_sup, P.capS);
+        if (tid == 0) { st_support += n_sup; st_maxsup = max(st_maxsup, (unsigned long long)n_sup); }
         // pass 0: exponent histogram of the compact reserve values (coalesced; no table access)
         for (int j = tid; j < n_sup; j += BLOCK) {
             const double x = sup_val[j];
@@ -526,24 +467,31 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         atomicAdd(P.stats + 0, st_edges);
         atomicAdd(P.stats + 1, st_frontier);
         atomicAdd(P.stats + 2, st_support);
+        atomicMax(P.max_support, st_maxsup);
         atomicAdd(P.cum + 0, st_edges);
         atomicAdd(P.cum + 1, st_frontier);
         atomicAdd(P.cum + 2, st_support);
         atomicAdd(P.cum + 3, st_sources);
-        atomicAdd(P.cum + 4, st_hash);
-        atomicAdd(P.cum + 5, st_fallback);
+    }
+}
+
+#include "gfpush_hash.cuh"
+
+// Hash-tier invariant between sources: every key empty, residues and reserves zero.
+__global__ void init_hash_kernel(int *keys, double *nxt, double *rsv, long long n_slots) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
+        keys[i] = kEmptyKey; nxt[i] = 0.0; rsv[i] = 0.0;
     }
 }
 
 // Table invariant between sources: next residue 0; epoch 0 never matches a source (epochs start at 1).
-__global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots, int4 *htab, long long n_hslots) {
+__global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
         if (tab16) tab16[i] = make_int4(0, 0, 0, 0);
         else meta8[i] = make_int2(0, 0);
     }
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_hslots; i += stride)
-        htab[i] = make_int4(0, 0, kEmptyKey, 0);
 }
 
 // CSR sanity: indptr[0]==0, non-decreasing, indptr[n]==nnz, 0 <= indices < n.
@@ -577,10 +525,25 @@ struct gp_graph {
     size_t scratch_bytes = 0;
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
-    int scratch_hash_slots = 0;
     long long epoch_base = 0;              // sources pushed since the tables were last initialised
     double *d_coef = nullptr;              // [kMaxLevels]
-    unsigned long long *d_ctrl = nullptr;  // [0] queue, [1..4] stats, [8..11] cumulative counters
+    // [0] queue [1..4] stats [5] hash-tier queue [6] redo count [7] redo queue [8] max support | [16..21] cumulative
+    unsigned long long *d_ctrl = nullptr;
+    // hash tier (HBM mode): chosen once per (L, rmax, coef) from a pilot run on the slabs
+    struct Tier {
+        bool valid = false, enabled = false;
+        int gen = -1, L = 0;
+        double rmax = 0.0, coef_sum = 0.0, coef0 = 0.0;
+        double avg_support = 0.0;
+        long long max_support = 0;
+        int G = 1, clusters = 0, Cmax = 0, block = 1024;
+        long long capP = 0, capL = 0;
+        size_t off_keys = 0, off_nxt = 0, off_rsv = 0, off_ps = 0, off_pd = 0, off_pv = 0, off_nid = 0, off_tk = 0, off_tv = 0;
+    } tier;
+    void *hscratch = nullptr;
+    size_t hscratch_bytes = 0;
+    int *d_redo = nullptr;
+    size_t d_redo_cap = 0;
     // staging for the host-buffer entry point
     int *d_node = nullptr;
     size_t d_node_cap = 0;
@@ -613,8 +576,7 @@ struct Plan {
     long long ctas, capF, capS;
     size_t dyn_smem;
     size_t bytes;
-    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand, off_htab, off_sup_slot;
-    int hash_slots;
+    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand;
 };
 
 int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
@@ -652,14 +614,6 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         per_sm = std::min(per_sm, fit);
     }
     long long ctas = (long long)g->num_sms * per_sm;  // scratch is sized for a full grid; small calls launch fewer
-    // Hash tier (HBM mode): 32 K slots = 512 KB per CTA, 76 MB for 148 CTAs -- inside the 126 MB L2 next to the
-    // compact per-CTA lists.  Pointless when even the bound on one level's frontier cannot fit.
-    int hash_slots = 0;
-    if (mode == GP_SCRATCH_HBM && g_push_hash_slots > 0 && n > g_push_hash_slots) {
-        hash_slots = g_push_hash_slots;
-        // when capS is a true bound on the support, a table of 1.6 x capS never overflows
-        while (hash_slots > 1024 && (long long)(hash_slots / 2) * 5 / 8 > capS) hash_slots /= 2;
-    }
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
         p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 8), 256);
@@ -669,8 +623,6 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         p->off_nxt_id = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_sup_id = o; o += align_up((size_t)c * capS * 4, 256);
         p->off_cand = o; o += align_up((size_t)c * capS * 8, 256);
-        p->off_htab = o; o += align_up((size_t)c * hash_slots * 16, 256);
-        p->off_sup_slot = o; o += align_up((size_t)c * (hash_slots ? capS : 0) * 4, 256);
         return o;
     };
     size_t budget = (size_t)g->cfg.max_scratch_bytes;
@@ -681,7 +633,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     }
     Plan tmp{};
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
-    pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS; pl->hash_slots = hash_slots;
+    pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
     pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : 0;
     pl->bytes = bytes_for(ctas, pl);
     GP_REQUIRE(pl->bytes <= budget || ctas == 1, "scratch does not fit the budget");
@@ -691,7 +643,6 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
 int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream) {
     const bool same = g->scratch && g->scratch_bytes >= pl.bytes && g->scratch_ctas == pl.ctas &&
                       g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode &&
-                      g->scratch_hash_slots == pl.hash_slots &&
                       g->epoch_base + S < (1ll << 31) - 2;  // epoch tags are int32: re-initialise before they wrap
     if (same) return GP_OK;
     if (g->scratch && g->scratch_bytes < pl.bytes) {
@@ -707,12 +658,10 @@ int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream
     char *base = (char *)g->scratch;
     init_tables_kernel<<<g->num_sms * 8, 256, 0, stream>>>(
         pl.mode == GP_SCRATCH_HBM ? (int4 *)(base + pl.off_tab) : nullptr,
-        pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n,
-        (int4 *)(base + pl.off_htab), pl.ctas * (long long)pl.hash_slots);
+        pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n);
     GP_CUDA_TRY(cudaGetLastError());
     g->epoch_base = 0;
     g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
-    g->scratch_hash_slots = pl.hash_slots;
     return GP_OK;
 }
 
@@ -731,6 +680,134 @@ int launch_push(const PushParams &P, const Plan &pl, cudaStream_t stream) {
     return GP_OK;
 }
 
+// ---- hash tier: launch helpers -------------------------------------------------------------------
+template <int BLOCK, bool MULTI>
+int hash_launch_config(int G, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, cudaStream_t stream) {
+    auto kernel = gfpush_hash_kernel<BLOCK, MULTI>;
+    if (G > 8) GP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    *cfg = cudaLaunchConfig_t{};
+    cfg->blockDim = dim3(BLOCK); cfg->gridDim = dim3((unsigned)G); cfg->dynamicSmemBytes = 0; cfg->stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg->attrs = attr; cfg->numAttrs = MULTI ? 1 : 0;
+    return GP_OK;
+}
+
+// How many clusters of G CTAs the device keeps resident.
+template <int BLOCK>
+int hash_max_clusters_t(gp_graph *g, int G, int *out) {
+    int per_sm = 0;
+    if (G == 1) {
+        GP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfpush_hash_kernel<BLOCK, false>, BLOCK, 0));
+        *out = g->num_sms * std::max(per_sm, 1);
+        return GP_OK;
+    }
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    int rc = hash_launch_config<BLOCK, true>(G, &cfg, attr, nullptr);
+    if (rc != GP_OK) return rc;
+    cfg.gridDim = dim3((unsigned)(g->num_sms / G * G));
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gfpush_hash_kernel<BLOCK, true>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *out = n;
+    return GP_OK;
+}
+int hash_max_clusters(gp_graph *g, int block, int G, int *out) {
+    return block == 512 ? hash_max_clusters_t<512>(g, G, out) : hash_max_clusters_t<1024>(g, G, out);
+}
+
+template <int BLOCK>
+int launch_hash_t(const HashParams &P, int G, int clusters, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    if (G == 1) {
+        gfpush_hash_kernel<BLOCK, false><<<(unsigned)clusters, BLOCK, 0, stream>>>(P);
+    } else {
+        int rc = hash_launch_config<BLOCK, true>(G, &cfg, attr, stream);
+        if (rc != GP_OK) return rc;
+        cfg.gridDim = dim3((unsigned)(clusters * G));
+        GP_CUDA_TRY(cudaLaunchKernelEx(&cfg, gfpush_hash_kernel<BLOCK, true>, P));
+    }
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+int launch_hash(const HashParams &P, int block, int G, int clusters, cudaStream_t stream) {
+    return block == 512 ? launch_hash_t<512>(P, G, clusters, stream) : launch_hash_t<1024>(P, G, clusters, stream);
+}
+
+// Chooses cluster size and table capacity from the pilot's support statistics and allocates the tier.
+int plan_tier(gp_graph *g, const Plan &pl, double avg_support, long long max_support, cudaStream_t stream) {
+    gp_graph::Tier &t = g->tier;
+    t.avg_support = avg_support; t.max_support = max_support;
+    t.enabled = false;
+    t.block = g_push_hash_block == 512 ? 512 : 1024;
+    const long long n = g->n;
+    // table capacity: twice the largest pilot support at the target load, never more than the graph needs
+    long long cmax = g_push_hash_slots > 0 ? g_push_hash_slots
+                                           : (long long)std::ceil(2.0 * (double)std::max<long long>(max_support, 256) * 100.0 / g_push_load_pct);
+    const long long cap_n = (long long)std::ceil((double)n * 100.0 / g_push_load_pct) + 1024;
+    cmax = std::min(cmax, cap_n);
+    cmax = std::max<long long>((cmax + 1023) / 1024 * 1024, 2048);
+    if (cmax > (1ll << 30)) return GP_OK;
+    // live bytes per source: 20 B per slot at a typical 55 % fill of the bound-sized table, plus the lists
+    const double live = 36.0 * std::max(avg_support, 64.0) + 16384.0;
+    const double budget = (double)g_push_l2_mb * 1048576.0;
+    int G = g_push_cluster, clusters = 0;
+    if (G == 0) {
+        const int cand[5] = {1, 2, 4, 8, 16};
+        int best = 0, best_clusters = 0;
+        for (int c : cand) {
+            int nc = 0;
+            int rc = hash_max_clusters(g, t.block, c, &nc);
+            if (rc != GP_OK) return rc;
+            if (nc <= 0) continue;
+            best = c; best_clusters = nc;
+            if ((double)nc * live <= budget) break;
+        }
+        G = best; clusters = best_clusters;
+        // a table per source that is not smaller than the slab buys nothing
+        if (G == 0 || cmax * 20 >= n * 16) return GP_OK;
+    } else {
+        GP_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8 || G == 16, "push_cluster must be 0, 1, 2, 4, 8 or 16");
+        int rc = hash_max_clusters(g, t.block, G, &clusters);
+        if (rc != GP_OK) return rc;
+        GP_REQUIRE(clusters > 0, "a cluster of %d CTAs x 1024 threads is not schedulable on this device", G);
+    }
+    if (g_push_max_clusters > 0) clusters = std::min(clusters, g_push_max_clusters);
+    t.G = G; t.clusters = clusters; t.Cmax = (int)cmax;
+    t.capP = std::min<long long>(pl.capF, cmax);
+    t.capL = cmax / std::max(g_push_list_div, 1) + 1024;
+    size_t o = 0;
+    const size_t c = (size_t)clusters;
+    t.off_keys = o; o += align_up(c * cmax * 4, 256);
+    t.off_nxt = o; o += align_up(c * cmax * 8, 256);
+    t.off_rsv = o; o += align_up(c * cmax * 8, 256);
+    t.off_ps = o; o += align_up(c * t.capP * 4, 256);
+    t.off_pd = o; o += align_up(c * t.capP * 4, 256);
+    t.off_pv = o; o += align_up(c * t.capP * 8, 256);
+    t.off_nid = o; o += align_up(c * t.capL * 4, 256);
+    t.off_tk = o; o += align_up(c * cmax * 4, 256);
+    t.off_tv = o; o += align_up(c * cmax * 8, 256);
+    if (g->hscratch_bytes < o) {
+        GP_CUDA_TRY(cudaStreamSynchronize(stream));
+        cudaFree(g->hscratch); g->hscratch = nullptr; g->hscratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&g->hscratch, o);
+        if (e != cudaSuccess) { cudaGetLastError(); return GP_OK; }  // no room: stay on the slabs
+        g->hscratch_bytes = o;
+    }
+    char *hb = (char *)g->hscratch;
+    init_hash_kernel<<<g->num_sms * 8, 256, 0, stream>>>((int *)(hb + t.off_keys), (double *)(hb + t.off_nxt),
+                                                         (double *)(hb + t.off_rsv), (long long)clusters * cmax);
+    GP_CUDA_TRY(cudaGetLastError());
+    t.enabled = true;
+    return GP_OK;
+}
+
+int launch_slab(const PushParams &P, const Plan &pl, cudaStream_t stream) {
+    return pl.block == 256 ? launch_push<256>(P, pl, stream)
+           : pl.block == 512 ? launch_push<512>(P, pl, stream)
+                             : launch_push<1024>(P, pl, stream);
+}
+
 int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const double *coef, int L, double rmax,
                        int K, int *d_row, int *d_col, double *d_val, float *d_val32, cudaStream_t stream) {
     GP_REQUIRE(S >= 0, "negative source count");
@@ -747,7 +824,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     rc = ensure_scratch(g, pl, S, stream);
     if (rc != GP_OK) return rc;
     GP_CUDA_TRY(cudaMemcpyAsync(g->d_coef, coef, sizeof(double) * L, cudaMemcpyHostToDevice, stream));
-    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 8, stream));
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 16, stream));
     char *base = (char *)g->scratch;
     PushParams P{};
     P.indptr = g->d_indptr; P.indices = g->d_indices; P.n = (int)g->n;
@@ -762,21 +839,90 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.nxt_id = (int *)(base + pl.off_nxt_id);
     P.sup_id = (int *)(base + pl.off_sup_id);
     P.sup_val = (double *)(base + pl.off_cand);
-    P.htab = (Slot *)(base + pl.off_htab);
-    P.sup_slot = (int *)(base + pl.off_sup_slot);
-    P.hash_slots = pl.hash_slots;
-    P.hash_shift = 32;
-    for (int h = pl.hash_slots; h > 1; h >>= 1) P.hash_shift--;
-    P.hash_limit = (int)std::min<long long>((long long)pl.hash_slots * 5 / 8, pl.capS - 1);
     P.capF = pl.capF; P.capS = pl.capS;
-    P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 8;
-    rc = pl.block == 256 ? launch_push<256>(P, pl, stream)
-         : pl.block == 512 ? launch_push<512>(P, pl, stream)
-                           : launch_push<1024>(P, pl, stream);
-    if (rc != GP_OK) return rc;
+    P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 16;
+    P.max_support = g->d_ctrl + 8;
+    P.redo = nullptr; P.redo_count = nullptr;
+    int launches = 0;
+    long long done = 0;  // sources [0, done) are finished by the pilot
+
+    // ---- tier choice (HBM mode only): pilot on the slabs once per (L, rmax, coef) and tuning generation
+    const bool want_hash = pl.mode == GP_SCRATCH_HBM && g_push_hash != 0;
+    if (want_hash) {
+        double csum = 0.0;
+        for (int i = 0; i < L; i++) csum += coef[i] * (double)(i + 1);
+        gp_graph::Tier &t = g->tier;
+        const bool same = t.valid && t.gen == g_push_tuning_gen && t.L == L && t.rmax == rmax && t.coef_sum == csum &&
+                          t.coef0 == coef[0];
+        if (!same) {
+            const long long pilot = std::min<long long>(S, std::max(g_push_pilot, 1));
+            if (S >= 2 * pilot) {
+                PushParams Q = P;
+                Q.S = pilot;
+                rc = launch_slab(Q, pl, stream);
+                if (rc != GP_OK) return rc;
+                launches++;
+                unsigned long long h[9];
+                GP_CUDA_TRY(cudaMemcpyAsync(h, g->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, stream));
+                GP_CUDA_TRY(cudaStreamSynchronize(stream));
+                t = gp_graph::Tier{};
+                t.valid = true; t.gen = g_push_tuning_gen; t.L = L; t.rmax = rmax; t.coef_sum = csum; t.coef0 = coef[0];
+                rc = plan_tier(g, pl, (double)h[3] / (double)pilot, (long long)h[8], stream);
+                if (rc != GP_OK) return rc;
+                done = pilot;
+            }
+        }
+    }
+    const bool use_hash = want_hash && g->tier.valid && g->tier.enabled && g->tier.gen == g_push_tuning_gen &&
+                          g->tier.L == L && g->tier.rmax == rmax;
+    if (done < S && use_hash) {
+        const gp_graph::Tier &t = g->tier;
+        const long long rest = S - done;
+        if (g->d_redo_cap < (size_t)rest) {
+            GP_CUDA_TRY(cudaStreamSynchronize(stream));
+            cudaFree(g->d_redo); g->d_redo = nullptr; g->d_redo_cap = 0;
+            GP_CUDA_TRY(cudaMalloc(&g->d_redo, sizeof(int) * (size_t)rest));
+            g->d_redo_cap = (size_t)rest;
+        }
+        char *hb = (char *)g->hscratch;
+        HashParams H{};
+        H.indptr = g->d_indptr; H.indices = g->d_indices; H.n = (int)g->n;
+        H.node_idx = d_node_idx + done; H.S = rest; H.coef = g->d_coef; H.L = L; H.rmax = rmax; H.K = K;
+        H.out_row = d_row + done * K; H.out_col = d_col + done * K; H.out_val = d_val + done * K;
+        H.out_val32 = d_val32 ? d_val32 + done * K : nullptr;
+        H.keys = (int *)(hb + t.off_keys); H.nxt = (double *)(hb + t.off_nxt); H.rsv = (double *)(hb + t.off_rsv);
+        H.push_start = (int *)(hb + t.off_ps); H.push_deg = (int *)(hb + t.off_pd); H.push_val = (double *)(hb + t.off_pv);
+        H.nxt_id = (int *)(hb + t.off_nid); H.tmp_key = (int *)(hb + t.off_tk); H.tmp_val = (double *)(hb + t.off_tv);
+        H.Cmax = t.Cmax; H.capP = t.capP; H.capL = t.capL;
+        H.load_pct = g_push_load_pct; H.list_div = std::max(g_push_list_div, 1);
+        H.redo = g->d_redo; H.redo_count = g->d_ctrl + 6;
+        H.queue = g->d_ctrl + 5; H.stats = g->d_ctrl + 1; H.cum = g->d_ctrl + 16; H.phase = g->d_ctrl + 24;
+        rc = launch_hash(H, t.block, t.G, (int)std::min<long long>(t.clusters, rest), stream);
+        if (rc != GP_OK) return rc;
+        launches++;
+        // second pass: whatever did not fit the tables, on the slabs (exits at once when the list is empty)
+        PushParams R = P;
+        R.node_idx = H.node_idx; R.S = rest;
+        R.out_row = H.out_row; R.out_col = H.out_col; R.out_val = H.out_val; R.out_val32 = H.out_val32;
+        R.epoch_base = (int)(g->epoch_base + done);
+        R.queue = g->d_ctrl + 7; R.redo = g->d_redo; R.redo_count = g->d_ctrl + 6;
+        rc = launch_slab(R, pl, stream);
+        if (rc != GP_OK) return rc;
+        launches++;
+    } else if (done < S) {
+        PushParams Q = P;
+        Q.node_idx = d_node_idx + done; Q.S = S - done;
+        Q.out_row = d_row + done * K; Q.out_col = d_col + done * K; Q.out_val = d_val + done * K;
+        Q.out_val32 = d_val32 ? d_val32 + done * K : nullptr;
+        Q.epoch_base = (int)(g->epoch_base + done);
+        Q.queue = g->d_ctrl + 7;
+        rc = launch_slab(Q, pl, stream);
+        if (rc != GP_OK) return rc;
+        launches++;
+    }
     g->epoch_base += S;
-    g->last.sources = S; g->last.ctas = std::min<long long>(pl.ctas, S); g->last.scratch_bytes = (int64_t)g->scratch_bytes;
-    g->last.scratch_mode = pl.mode; g->last.kernel_launches = 1;
+    g->last.sources = S; g->last.ctas = std::min<long long>(pl.ctas, S); g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->hscratch_bytes);
+    g->last.scratch_mode = pl.mode; g->last.kernel_launches = launches;
     return GP_OK;
 }
 
@@ -800,10 +946,10 @@ int graph_finish_create(gp_graph *g) {
     g->smem_optin = prop.sharedMemPerBlockOptin;
     GP_CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     GP_CUDA_TRY(cudaMalloc(&g->d_coef, sizeof(double) * kMaxLevels));
-    GP_CUDA_TRY(cudaMalloc(&g->d_ctrl, sizeof(unsigned long long) * 16));
+    GP_CUDA_TRY(cudaMalloc(&g->d_ctrl, sizeof(unsigned long long) * 32));
     // validate the CSR once, on the device (the reference validates nothing)
     int *d_flag = (int *)(g->d_ctrl);
-    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 16, g->stream));
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 32, g->stream));
     validate_csr_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(g->d_indptr, g->n, g->d_indices, g->nnz, d_flag);
     GP_CUDA_TRY(cudaGetLastError());
     int flag = 0;
@@ -869,7 +1015,7 @@ void gp_graph_destroy(gp_graph *g) {
     DeviceGuard guard(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->owns_csr) { cudaFree(g->d_indptr); cudaFree(g->d_indices); }
-    cudaFree(g->scratch); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
+    cudaFree(g->scratch); cudaFree(g->hscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }
@@ -935,12 +1081,22 @@ int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset) {
     DeviceGuard guard(g->device);
     GP_CUDA_TRY(cudaDeviceSynchronize());
     unsigned long long h[6];
-    GP_CUDA_TRY(cudaMemcpy(h, g->d_ctrl + 8, sizeof h, cudaMemcpyDeviceToHost));
-    if (reset) GP_CUDA_TRY(cudaMemset(g->d_ctrl + 8, 0, sizeof h));
+    GP_CUDA_TRY(cudaMemcpy(h, g->d_ctrl + 16, sizeof h, cudaMemcpyDeviceToHost));
+    if (reset) GP_CUDA_TRY(cudaMemset(g->d_ctrl + 16, 0, sizeof h));
     *out = g->last;
     out->edges_pushed = (int64_t)h[0]; out->frontier_total = (int64_t)h[1];
     out->support_total = (int64_t)h[2]; out->sources = (int64_t)h[3];
     out->hash_sources = (int64_t)h[4]; out->hash_fallbacks = (int64_t)h[5];
+    return GP_OK;
+}
+
+int gp_gfpush_phase_cycles(gp_graph *g, uint64_t out[8], int reset) {
+    GP_REQUIRE(g && out, "null argument");
+    std::lock_guard<std::mutex> lk(g->mu);
+    DeviceGuard guard(g->device);
+    GP_CUDA_TRY(cudaDeviceSynchronize());
+    GP_CUDA_TRY(cudaMemcpy(out, g->d_ctrl + 24, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost));
+    if (reset) GP_CUDA_TRY(cudaMemset(g->d_ctrl + 24, 0, sizeof(uint64_t) * 8));
     return GP_OK;
 }
 

@@ -142,6 +142,13 @@ class Graph:
         return st.as_dict()
 
 
+    def phase_cycles(self, reset=False) -> dict:
+        """SM cycles per phase of the hash tier's leader CTAs (profiling hook)."""
+        out = (ctypes.c_uint64 * 8)()
+        _lib.check(self._lib.gp_gfpush_phase_cycles(self._h, ctypes.byref(out), int(bool(reset))))
+        names = ("fetch", "grow", "expand", "settle", "topk", "wide_expand", "wide_settle", "resident")
+        return dict(zip(names, [int(x) for x in out]))
+
     def cumulative_stats(self, reset=False) -> dict:
         st = _lib.PushStats()
         _lib.check(self._lib.gp_gfpush_cumulative_stats(self._h, ctypes.byref(st), int(bool(reset))))

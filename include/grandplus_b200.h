@@ -106,12 +106,18 @@ typedef struct {
     int32_t scratch_mode;    /* mode actually used (gp_scratch_mode)                  */
     int32_t kernel_launches; /* kernels launched by the call                          */
     int64_t hash_sources;    /* cumulative stats only: sources finished on the L2-resident hash tier  */
-    int64_t hash_fallbacks;  /* cumulative stats only: sources restarted on the direct-addressed table */
+    int64_t hash_fallbacks;  /* cumulative stats only: sources handed over to the direct-addressed slabs */
 } gp_push_stats;
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out);
 /* Counters summed over every gfpush since creation / the last reset (device-wide synchronise);
  * lets a caller time a burst of asynchronous calls and read the work afterwards. */
 int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset);
+
+/* Profiling hook (the reference only takes an unused gettimeofday pair, graph.h:54-56,129-130): SM cycles the
+ * leader CTAs of the hash tier spent per phase, summed over CTAs since the last reset:
+ * [0] fetch + level 0, [1] table growth, [2] expand, [3] settle, [4] top-k, [5] expand of each source's widest
+ * level, [6] its settle, [7] kernel residency.  Device-wide synchronise. */
+int gp_gfpush_phase_cycles(gp_graph *g, uint64_t out[8], int reset);
 
 /* ------------------------------------------------------------------------------------------
  * Part 2: fused gather - mask - scale - reduce aggregation (all pointers DEVICE)
@@ -190,8 +196,9 @@ int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, 
 
 /* Performance knobs for sweeps (profiles/); defaults are the measured best.  Keys: "agg_kernel"
  * (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf", "agg_max_vec",
- * "agg_max_chunk", "agg_smem_kb", "push_hash_slots" (slots of GFPush's L2-resident hash tier, 0 = off).
- * Results never depend on them. */
+ * "agg_max_chunk", "agg_smem_kb"; GFPush's L2-resident hash tier: "push_hash" (0 = slabs only), "push_cluster"
+ * (CTAs per source: 0 auto, 1, 2, 4, 8, 16), "push_hash_slots" (table capacity per cluster, 0 auto), "push_l2_mb",
+ * "push_load_pct", "push_list_div", "push_pilot".  Results never depend on them. */
 int gp_set_tuning(const char *key, int64_t value);
 
 #ifdef __cplusplus

@@ -199,41 +199,100 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
     assert same > 0.8 * n
 
 
-@pytest.mark.parametrize("slots", [0, 1024, 32768])
-def test_gfpush_hash_tier_on_off_and_fallback(slots):
-    """The L2-resident hash tier, the direct-addressed table, and the restart from one to the other
-    (a 1024-slot table overflows for most sources) must all give the oracle's rows and work counters."""
-    from grandplus_b200 import _lib, synth
+class _tuning:
+    """Scoped gp_set_tuning: restores the defaults on exit."""
+    DEFAULTS = {"push_hash": 1, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
+                "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0}
+
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        from grandplus_b200 import _lib
+        for k, v in self.kv.items():
+            _lib.set_tuning(k, v)
+
+    def __exit__(self, *exc):
+        from grandplus_b200 import _lib
+        for k in self.kv:
+            _lib.set_tuning(k, self.DEFAULTS[k])
+
+
+# (push_hash, push_cluster, push_hash_slots): slabs only / one CTA per source / clusters of 2..16 CTAs per
+# source over DSMEM / a table so small that most sources are handed over to the slabs
+TIERS = [(0, 0, 0), (1, 1, 0), (1, 2, 0), (1, 4, 0), (1, 8, 0), (1, 16, 0), (1, 1, 2048), (1, 4, 2048)]
+
+
+@pytest.mark.parametrize("tier", TIERS)
+def test_gfpush_hash_tier_clusters_and_handover(tier):
+    """The L2-resident hash tier at every cluster size, the direct-addressed slabs, and the hand-over from
+    one to the other must all give the oracle's rows and the oracle's work counters."""
+    from grandplus_b200 import synth
+    use_hash, cluster, slots = tier
     indptr, indices = synth.powerlaw_csr(60_000, 700_000, seed=5)
     indptr, indices = indptr.numpy(), indices.numpy()
-    src = synth.sources(60_000, 300, seed=4).numpy()
+    src = synth.sources(60_000, 400, seed=4).numpy()
     coef = og.coef_for("ppr", 6, 0.05)
-    _lib.set_tuning("push_hash_slots", slots)
-    try:
+    with _tuning(push_hash=use_hash, push_cluster=cluster, push_hash_slots=slots, push_pilot=16):
         g = _graph(indptr, indices, scratch_mode=HBM)
         g.cumulative_stats(reset=True)
         row, col, val = _run(g, src, coef, 1e-5, 32)
         st = g.cumulative_stats()
-    finally:
-        _lib.set_tuning("push_hash_slots", 32768)
-    worst = check_topk_rows(indptr, indices, src, coef, 1e-5, 32, col, val, row=row, max_rows=100)
+        # the tables must be clean afterwards: a second run on the same handle gives the same rows
+        row2, col2, val2 = _run(g, src, coef, 1e-5, 32)
+        st2 = g.cumulative_stats()
+    worst = check_topk_rows(indptr, indices, src, coef, 1e-5, 32, col, val, row=row, max_rows=120)
     assert worst < 1e-11
     _, _, _, ost = og.gfpush(indptr, indices, src, coef, 1e-5, 32)
-    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * ost.edges_pushed      # restarted work is not double counted
+    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * ost.edges_pushed      # handed-over work is not double counted
     assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
+    assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
     assert st["sources"] == len(src)
-    if slots == 0:
+    if not use_hash:
         assert st["hash_sources"] == 0 and st["hash_fallbacks"] == 0
-    elif slots == 1024:
-        assert st["hash_fallbacks"] > 0
+    elif slots:
+        assert st["hash_fallbacks"] > 0 and st["hash_sources"] + st["hash_fallbacks"] == len(src) - 16
     else:
         assert st["hash_sources"] > 0.5 * len(src)
-    # the tables must be clean afterwards: a second run on the same handle gives the same rows
-    _lib.set_tuning("push_hash_slots", slots)
-    try:
-        row2, col2, val2 = _run(g, src, coef, 1e-5, 32)
-    finally:
-        _lib.set_tuning("push_hash_slots", 32768)
+    assert st2["sources"] == 2 * len(src)
+    assert abs(st2["edges_pushed"] - 2 * ost.edges_pushed) <= 2e-6 * ost.edges_pushed
     for (ac, av), (bc, bv) in zip(og.rows_as_sets(col, val, 32), og.rows_as_sets(col2, val2, 32)):
         if np.array_equal(ac, bc):
             np.testing.assert_allclose(av, bv, rtol=1e-12)
+
+
+@pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("citeseer", "avg"), ("pubmed", "ppr"), ("pubmed", "single")])
+@pytest.mark.parametrize("cluster", [1, 4])
+def test_gfpush_hash_tier_matches_reference_golden(name, mode, cluster):
+    """Real graphs through the hash tier (forced: these graphs are small enough that auto keeps the slabs)."""
+    indptr, indices = load_graph(name)
+    z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
+    K, rmax = int(z["K"]), float(z["rmax"])
+    with _tuning(push_cluster=cluster, push_pilot=8):
+        g = _graph(indptr, indices, scratch_mode=HBM)
+        g.cumulative_stats(reset=True)
+        row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
+        st = g.cumulative_stats()
+    assert st["hash_sources"] + st["hash_fallbacks"] == len(z["node_idx"]) - 8
+    assert st["hash_sources"] > 0
+    worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
+    assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("name", ["path8", "star33", "isolated", "dangling"])
+def test_gfpush_hash_tier_tiny_graphs(name):
+    """Dangling nodes, K > support, degree-1 nodes: the edge cases of graph.h:91-93,113,121 on the hash tier."""
+    z = np.load(os.path.join(GOLDEN, f"tiny_{name}.npz"))
+    reps = 6                                       # enough sources for the pilot + the tier
+    src = np.tile(z["node_idx"], reps)
+    with _tuning(push_cluster=2, push_pilot=1):
+        g = _graph(z["indptr"], z["indices"], scratch_mode=HBM)
+        for tag in sorted({k.split("/")[0] for k in z.files if "/" in k}):
+            K, rmax, coef = int(z[f"{tag}/K"]), float(z[f"{tag}/rmax"]), z[f"{tag}/coef"]
+            g.cumulative_stats(reset=True)
+            row, col, val = _run(g, src, coef, rmax, K)
+            st = g.cumulative_stats()
+            assert st["hash_sources"] == len(src) - 1, (tag, st)
+            check_topk_rows(z["indptr"], z["indices"], src, coef, rmax, K, col, val, row=row)
+            ref_filled = np.tile((z[f"{tag}/value"].reshape(-1, K) > 0).sum(1), reps)
+            np.testing.assert_array_equal((val.reshape(-1, K) > 0).sum(1), ref_filled)

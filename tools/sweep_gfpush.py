@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Sweep GFPush tier settings on one workload (GPU box).  Prints rows/s per configuration.
+
+    python tools/sweep_gfpush.py reddit "push_hash=0" "push_cluster=1" "push_cluster=2,push_load_pct=60" ...
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from grandplus_b200 import _lib  # noqa: E402
+from grandplus_b200.precompute import propagation  # noqa: E402
+
+DEFAULTS = {"push_hash": 1, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
+            "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0}
+
+
+def main():
+    name = sys.argv[1]
+    configs = sys.argv[2:] or ["push_hash=0", "push_cluster=0"]
+    steps = int(os.environ.get("SWEEP_STEPS", "4"))
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    w = bench.WORKLOADS[name]
+    S = int(os.environ.get("SWEEP_SOURCES", w["S"]))
+    indptr, indices, n = bench.build_workload(name, dev)
+    S = min(S, n)
+    coef = bench.coef_for(w["mode"], w["order"], w["alpha"])
+    batches = bench.source_batches(n, S, steps + 2, 0, 1, dev)
+    graph = propagation.Graph.from_device_csr(indptr, indices)
+    if os.environ.get("SWEEP_SCRATCH"):
+        graph.configure(scratch_mode=int(os.environ["SWEEP_SCRATCH"]))
+    for cfg in configs:
+        kv = dict(DEFAULTS)
+        for item in cfg.split(","):
+            if item:
+                k, v = item.split("=")
+                kv[k] = int(v)
+        for k, v in kv.items():
+            _lib.set_tuning(k, v)
+        for i in range(2):
+            graph.gfpush_device(batches[i], coef, w["rmax"], w["K"], want_fp32=True)
+        torch.cuda.synchronize()
+        graph.cumulative_stats(reset=True)
+        graph.phase_cycles(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            graph.gfpush_device(batches[2 + i], coef, w["rmax"], w["K"], want_fp32=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 1e3
+        st = graph.cumulative_stats(reset=True)
+        print(f"{name} S={S} {cfg:40s} rows/s={S * steps / t:12.0f}  edges/s={st['edges_pushed'] / t / 1e9:7.2f}G  "
+              f"hash={st['hash_sources']} redo={st['hash_fallbacks']} sup/src={st['support_total'] / max(st['sources'], 1):.0f} "
+              f"scratch={st['scratch_bytes'] / 1e6:.0f}MB", flush=True)
+        ph = graph.phase_cycles(reset=True)
+        if ph["resident"]:
+            print("    phases (% of leader-CTA residency): " +
+                  " ".join(f"{k}={100.0 * v / ph['resident']:.1f}" for k, v in ph.items() if k != "resident"), flush=True)
+    for k, v in DEFAULTS.items():
+        _lib.set_tuning(k, v)
+
+
+if __name__ == "__main__":
+    t0 = time.time()
+    main()
+    print(f"sweep wall {time.time() - t0:.1f}s")
