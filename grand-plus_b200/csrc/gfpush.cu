@@ -32,7 +32,8 @@
 #include <vector>
 
 // tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
-int g_push_hash = 1;          // "push_hash": 0 = direct-addressed slabs only
+int g_push_hash = 0;          // "push_hash": 1 = route HBM-mode sources through the L2-resident hash tier first
+                              // (opt-in: measured slower than the slabs on every BASELINE shape, profiles/r01_hash_tier.md)
 int g_push_cluster = 0;       // "push_cluster": CTAs per source (1,2,4,8,16), 0 = from the pilot statistics
 int g_push_hash_slots = 0;    // "push_hash_slots": table capacity per cluster, 0 = from the pilot statistics
 int g_push_l2_mb = 48;        // "push_l2_mb": L2 budget the live tables should fit

@@ -201,7 +201,7 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
-    DEFAULTS = {"push_hash": 1, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
+    DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
                 "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0}
 
     def __init__(self, **kv):
@@ -268,7 +268,7 @@ def test_gfpush_hash_tier_matches_reference_golden(name, mode, cluster):
     indptr, indices = load_graph(name)
     z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
     K, rmax = int(z["K"]), float(z["rmax"])
-    with _tuning(push_cluster=cluster, push_pilot=8):
+    with _tuning(push_hash=1, push_cluster=cluster, push_pilot=8):
         g = _graph(indptr, indices, scratch_mode=HBM)
         g.cumulative_stats(reset=True)
         row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
@@ -285,7 +285,7 @@ def test_gfpush_hash_tier_tiny_graphs(name):
     z = np.load(os.path.join(GOLDEN, f"tiny_{name}.npz"))
     reps = 6                                       # enough sources for the pilot + the tier
     src = np.tile(z["node_idx"], reps)
-    with _tuning(push_cluster=2, push_pilot=1):
+    with _tuning(push_hash=1, push_cluster=2, push_pilot=1):
         g = _graph(z["indptr"], z["indices"], scratch_mode=HBM)
         for tag in sorted({k.split("/")[0] for k in z.files if "/" in k}):
             K, rmax, coef = int(z[f"{tag}/K"]), float(z[f"{tag}/rmax"]), z[f"{tag}/coef"]

@@ -16,13 +16,13 @@ import bench  # noqa: E402
 from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
-DEFAULTS = {"push_hash": 1, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
+DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
             "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0}
 
 
 def main():
     name = sys.argv[1]
-    configs = sys.argv[2:] or ["push_hash=0", "push_cluster=0"]
+    configs = sys.argv[2:] or ["push_hash=0", "push_hash=1"]
     steps = int(os.environ.get("SWEEP_STEPS", "4"))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
