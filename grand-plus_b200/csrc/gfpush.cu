@@ -32,6 +32,9 @@
 #include <vector>
 
 // tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
+int g_push_smem_hash = 0;     // "push_smem_hash": 1 = shared-memory hash table in front of the slabs (HBM mode, MODE 2 kernel);
+                              // opt-in: measured 10-25 % slower than the plain slabs (profiles/r01_hash_tier.md)
+int g_push_smem_probe = 16;   // "push_smem_probe": probes before a node is sent to the slab
 int g_push_hash = 0;          // "push_hash": 1 = route HBM-mode sources through the L2-resident hash tier first
                               // (opt-in: measured slower than the slabs on every BASELINE shape, profiles/r01_hash_tier.md)
 int g_push_cluster = 0;       // "push_cluster": CTAs per source (1,2,4,8,16), 0 = from the pilot statistics
@@ -41,6 +44,7 @@ int g_push_load_pct = 60;     // "push_load_pct": (support bound)/(table size) t
 int g_push_list_div = 8;      // "push_list_div": levels with fewer than C/list_div edges settle via the first-touch list
 int g_push_hash_block = 1024; // "push_hash_block": threads per CTA of the hash tier (512 or 1024)
 int g_push_max_clusters = 0;  // "push_max_clusters": cap on concurrently processed sources of the hash tier (0 = all SMs)
+int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments
 int g_push_pilot = 256;       // "push_pilot": sources pushed on the slabs to measure the support before choosing G
 int g_push_tuning_gen = 0;    // bumped by gp_set_tuning so that handles re-plan
 
@@ -94,6 +98,11 @@ struct PushParams {
     const int *redo;
     const unsigned long long *redo_count;
     unsigned long long *max_support;  // largest reserve support of any source of this launch (pilot statistics)
+    unsigned long long *phase;        // SM cycles per phase, summed over CTAs (see gp_gfpush_phase_cycles)
+    // MODE 2 (shared-memory hash in front of the slabs): reserve of the nodes resident in shared memory,
+    double *rsv_g;     // [ctas][hslots], parallel to the shared-memory table slots (coalesced, L2-resident)
+    int hslots;        // power of two
+    int max_probe;     // a node that finds no slot within this many probes lives on the slab for this source
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -109,6 +118,9 @@ struct PushSmem {
     int bid[kBucketCap];
     long long it;
     int n_push, n_nxt, n_sup, n_out, n_bucket;
+    int n_tab;   // MODE 2: nodes resident in the shared-memory table
+    long long ph[8], t_prev, wide_expand, wide_settle;   // thread 0: cycles per phase (gp_gfpush_phase_cycles)
+    unsigned wide_E;
     int sel_bin, sel_above, sel_inbin;
 };
 
@@ -127,6 +139,33 @@ __device__ __forceinline__ long long warp_append_pos(bool is_new, long long cap,
     const long long pos = base + __popc(m & ((1u << lane) - 1u));
     if (pos >= cap) { atomicOr(err, kErrOverflow); return -1; }
     return pos;
+}
+
+// The same for U flags per lane with ONE atomic per warp: same-address shared-memory atomics from the 32 warps
+// of a CTA serialise, and the append counters were the hottest addresses of both phases.  Positions are assigned
+// flag-major (all lanes' flag 0 first).  Must be called by all 32 lanes.
+template <int U>
+__device__ __forceinline__ void warp_append_multi(const bool (&is_new)[U], long long cap, int *s_count,
+                                                  unsigned long long *err, long long (&pos)[U]) {
+    unsigned m[U];
+    int total = 0;
+#pragma unroll
+    for (int q = 0; q < U; q++) { m[q] = __ballot_sync(0xffffffffu, is_new[q]); total += __popc(m[q]); }
+#pragma unroll
+    for (int q = 0; q < U; q++) pos[q] = -1;
+    if (total == 0) return;
+    const int lane = gp_lane();
+    int base = 0;
+    if (lane == 0) base = atomicAdd(s_count, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int q = 0; q < U; q++) {
+        if (is_new[q]) {
+            const long long p = base + __popc(m[q] & ((1u << lane) - 1u));
+            if (p >= cap) atomicOr(err, kErrOverflow); else pos[q] = p;
+        }
+        base += __popc(m[q]);
+    }
 }
 
 // Largest t in [0, BLOCK) with off[t] <= e (off is a non-decreasing exclusive scan, off[0] == 0).
@@ -222,10 +261,22 @@ struct Tables {
     }
 };
 
-template <int BLOCK, bool SMEM_NXT>
+// MODE 0: direct-addressed slabs in HBM.  MODE 1: dense next-residue array in shared memory (small graphs).
+// MODE 2: open-addressed {key, next residue} table in SHARED MEMORY in front of the slabs: a node lives in the
+//   table for the whole source if it finds a slot within max_probe probes when it is first touched, otherwise on
+//   the slab (both decisions are stable: entries are never removed while the source is live).  Table hits cost
+//   shared-memory atomics (measured 1.18 find-or-claim + fp64 add per clock per SM,
+//   profiles/r01_smem_atomics_microbench.txt) instead of a DRAM round trip, settle walks the table instead of
+//   a list, and the reserve of table residents is a global array parallel to the slots (coalesced).
+template <int BLOCK, int MODE>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams P) {
+    constexpr bool SMEM_NXT = MODE == 1;
+    constexpr bool SHASH = MODE == 2;
     __shared__ PushSmem<BLOCK> sm;
     extern __shared__ double s_nxt_dyn[];
+    int *s_keys = reinterpret_cast<int *>(s_nxt_dyn + (SHASH ? P.hslots : 0));  // SHASH: [hslots] after the residues
+    const unsigned hmask = (unsigned)(P.hslots - 1);
+    double *rsv_g = SHASH ? P.rsv_g + (long long)blockIdx.x * P.hslots : nullptr;
 
     const int tid = threadIdx.x;
     const int lane = gp_lane();
@@ -245,13 +296,33 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     if (SMEM_NXT) {
         for (int i = tid; i < P.n; i += BLOCK) s_nxt_dyn[i] = 0.0;
     }
+    if (SHASH) {
+        for (int i = tid; i < P.hslots; i += BLOCK) { s_nxt_dyn[i] = 0.0; s_keys[i] = -1; }
+    }
+    // SHASH: slot of node v in the shared-memory table (claiming one if v is new), or -1 = v lives on the slab
+    auto s_find = [&](int v, bool &claimed) -> int {
+        claimed = false;
+        unsigned h = ((unsigned)v * 2654435761u) >> 7 & hmask;
+        for (int probe = 0; probe < P.max_probe; probe++, h = (h + 1) & hmask) {
+            int k = s_keys[h];
+            if (k == -1) {
+                k = atomicCAS(s_keys + h, -1, v);
+                if (k == -1) { claimed = true; return (int)h; }
+            }
+            if (k == v) return (int)h;
+        }
+        return -1;
+    };
     unsigned long long st_edges = 0, st_frontier = 0, st_support = 0, st_sources = 0, st_maxsup = 0;  // thread 0 only
+    const long long t_begin = clock64();
+    if (tid == 0) { for (int i = 0; i < 8; i++) sm.ph[i] = 0; sm.t_prev = t_begin; }
+#define GP_PHASE(i) do { if (tid == 0) { const long long t_now = clock64(); sm.ph[i] += t_now - sm.t_prev; sm.t_prev = t_now; } } while (0)
 
     for (;;) {
         __syncthreads();
         if (tid == 0) {
             sm.it = (long long)atomicAdd(P.queue, 1ull);
-            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0;
+            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0; sm.n_tab = 0;
         }
         __syncthreads();
         long long it = sm.it;
@@ -269,8 +340,14 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         // level 0: residue = {src: 1}, reserve = {src: 0} (graph.h:80-81); settle it right away
         if (tid == 0) {
             st_sources++; st_frontier++;
-            T.put(src, epoch, 0, true);
-            sup_id[0] = src; sup_val[0] = P.coef[0]; sm.n_sup = 1;
+            if (SHASH) {   // the table is empty: the source claims its home slot
+                bool claimed;
+                const int h = s_find(src, claimed);
+                rsv_g[h] = P.coef[0]; sm.n_tab = 1;
+            } else {
+                T.put(src, epoch, 0, true);
+                sup_id[0] = src; sup_val[0] = P.coef[0]; sm.n_sup = 1;
+            }
             if (P.L > 1) {
                 const int a = P.indptr[src], b = P.indptr[src + 1];
                 const unsigned d = (unsigned)(b - a);
@@ -279,12 +356,16 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             }
         }
         __syncthreads();
+        GP_PHASE(0);
+        if (tid == 0) { sm.wide_expand = 0; sm.wide_settle = 0; sm.wide_E = 0; }
 
         for (int level = 0; level < P.L - 1; level++) {  // graph.h:83
             // ---------------------------------------------------------------- expand (graph.h:94-100)
             // Only nodes that passed r >= rmax*deg are in the push list.  A tile of BLOCK of them is
             // prefix-summed by degree and the tile's edges are dealt to threads by rank.
             const int n_push = sm.n_push;
+            int n_claims = 0;
+            unsigned lvl_E = 0;
             for (int base = 0; base < n_push; base += BLOCK) {
                 const int j = base + tid;
                 unsigned d_push = 0;
@@ -295,7 +376,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
                 __syncthreads();
-                if (tid == 0) st_edges += total;
+                if (tid == 0) { st_edges += total; lvl_E += total; }
                 // edge e of the tile goes to thread e % BLOCK: every warp gets work as soon as the tile has
                 // BLOCK edges, and a warp's 32 lanes read 32 consecutive `indices` entries
                 for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += BLOCK * kEdgeUnroll) {
@@ -315,17 +396,45 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         }
                     }
                     bool fresh[kEdgeUnroll];
+                    int entry[kEdgeUnroll];   // what the frontier list stores: node id (slab resident) or ~slot (table resident)
+                    if (SHASH) {
+                        int h[kEdgeUnroll];
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next(v[q], add[q]);
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            h[q] = -1;
+                            bool claimed = false;
+                            if (ok[q]) h[q] = s_find(v[q], claimed);
+                            n_claims += claimed ? 1 : 0;
+                        }
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) {
-                        const long long pos = warp_append_pos(fresh[q], P.capF, &sm.n_nxt, err);
-                        if (pos >= 0) nxt_id[pos] = v[q];
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            fresh[q] = false; entry[q] = v[q];
+                            if (ok[q]) {
+                                if (h[q] >= 0) { fresh[q] = atomicAdd(s_nxt_dyn + h[q], add[q]) == 0.0; entry[q] = ~h[q]; }
+                                else fresh[q] = T.add_next(v[q], add[q]);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) { fresh[q] = ok[q] && T.add_next(v[q], add[q]); entry[q] = v[q]; }
                     }
+                    long long lpos[kEdgeUnroll];
+                    warp_append_multi<kEdgeUnroll>(fresh, P.capF, &sm.n_nxt, err, lpos);
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++)
+                        if (lpos[q] >= 0) nxt_id[lpos[q]] = entry[q];
                 }
                 __syncthreads();
             }
+            if (SHASH) {
+                n_claims = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_claims);
+                if (lane == 0 && n_claims) atomicAdd(&sm.n_tab, n_claims);
+                n_claims = 0;
+            }
             if (n_push == 0) __syncthreads();
+            long long t_e = 0;
+            if (tid == 0) t_e = clock64() - sm.t_prev;
+            GP_PHASE(1);
             // ---------------------------------------------------------------- settle (graph.h:85-93,102)
             // Every node of the new frontier, independently: take its residue, credit the reserve,
             // and decide now whether it will push at the next level.
@@ -345,57 +454,94 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     ok[q] = j < n_nxt;
                     v[q] = ok[q] ? nxt_id[j] : 0;
                 }
-                double x[kSettleUnroll];
-                int pos[kSettleUnroll];
+                double x[kSettleUnroll], r0[kSettleUnroll];
+                int pos[kSettleUnroll], hs[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    pos[q] = 0; x[q] = 0.0;
-                    if (ok[q]) x[q] = T.take(v[q], epoch, pos[q]);
+                    pos[q] = 0; x[q] = 0.0; r0[q] = 0.0; hs[q] = -1;
+                    if (ok[q]) {
+                        if (SHASH && v[q] < 0) {   // table resident: residue and key in shared memory, reserve in rsv_g
+                            hs[q] = ~v[q];
+                            x[q] = s_nxt_dyn[hs[q]]; s_nxt_dyn[hs[q]] = 0.0;
+                            v[q] = s_keys[hs[q]];
+                            r0[q] = __ldcg(rsv_g + hs[q]);
+                        } else {
+                            x[q] = T.take(v[q], epoch, pos[q]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
                     a[q] = 0; b[q] = 0;
                     if (ok[q] && will_push) { a[q] = __ldg(P.indptr + v[q]); b[q] = __ldg(P.indptr + v[q] + 1); }
                 }
+                // reserve[v] += coef * r (graph.h:90): rsv_g for table residents, the compact support arrays otherwise
+                bool tbl[kSettleUnroll], first[kSettleUnroll], push[kSettleUnroll];
+                int st[kSettleUnroll], dg[kSettleUnroll];
+                double val[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    // reserve[v] += coef * r (graph.h:90), in the compact support arrays
-                    const bool first = ok[q] && pos[q] < 0;
-                    const long long ps = warp_append_pos(first, P.capS, &sm.n_sup, err);
-                    if (first) {
-                        if (ps >= 0) { sup_id[ps] = v[q]; sup_val[ps] = c * x[q]; }
-                        T.put(v[q], epoch, (int)max(ps, 0ll), true);
+                    tbl[q] = SHASH && hs[q] >= 0;
+                    first[q] = ok[q] && !tbl[q] && pos[q] < 0;
+                    push[q] = false; st[q] = -1; dg[q] = 1; val[q] = x[q];
+                    if (ok[q] && will_push) {
+                        const unsigned d = (unsigned)(b[q] - a[q]);
+                        if (d == 0) push[q] = true;                                   // graph.h:91-93: back to the source
+                        else if (x[q] >= P.rmax * (double)d) {                        // graph.h:94
+                            push[q] = true; st[q] = a[q]; dg[q] = (int)d; val[q] = x[q] / (double)d;  // graph.h:95
+                        }
+                    }
+                }
+                long long ps[kSettleUnroll], pp[kSettleUnroll];
+                warp_append_multi<kSettleUnroll>(first, P.capS, &sm.n_sup, err, ps);
+                warp_append_multi<kSettleUnroll>(push, P.capF, &sm.n_push, err, pp);
+#pragma unroll
+                for (int q = 0; q < kSettleUnroll; q++) {
+                    if (tbl[q]) {
+                        rsv_g[hs[q]] = r0[q] + c * x[q];
+                    } else if (first[q]) {
+                        if (ps[q] >= 0) { sup_id[ps[q]] = v[q]; sup_val[ps[q]] = c * x[q]; }
+                        T.put(v[q], epoch, (int)max(ps[q], 0ll), true);
                     } else if (ok[q]) {
                         sup_val[pos[q]] += c * x[q];
                         T.put(v[q], epoch, pos[q], false);
                     }
-                    bool push = false;
-                    int st = -1, dg = 1;
-                    double val = x[q];
-                    if (ok[q] && will_push) {
-                        const unsigned d = (unsigned)(b[q] - a[q]);
-                        if (d == 0) push = true;                                   // graph.h:91-93: back to the source
-                        else if (x[q] >= P.rmax * (double)d) {                     // graph.h:94
-                            push = true; st = a[q]; dg = (int)d; val = x[q] / (double)d;  // graph.h:95
-                        }
-                    }
-                    const long long pp = warp_append_pos(push, P.capF, &sm.n_push, err);
-                    if (pp >= 0) { push_start[pp] = st; push_deg[pp] = dg; push_val[pp] = val; }
+                    if (pp[q] >= 0) { push_start[pp[q]] = st[q]; push_deg[pp[q]] = dg[q]; push_val[pp[q]] = val[q]; }
                 }
             }
             __syncthreads();
-            if (tid == 0) sm.n_nxt = 0;
+            if (tid == 0) {
+                sm.n_nxt = 0;
+                if (lvl_E >= sm.wide_E) { sm.wide_E = lvl_E; sm.wide_expand = t_e; sm.wide_settle = clock64() - sm.t_prev; }
+            }
+            GP_PHASE(2);
             __syncthreads();
         }
+        if (tid == 0) { sm.ph[5] += sm.wide_expand; sm.ph[6] += sm.wide_settle; }
         for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
+        if (SHASH) {
+            // stage the reserve of the table residents in the (now all-zero) shared residue array: the radix passes
+            // below then read shared memory only; the global copy is wiped on the way
+            for (int j = tid; j < P.hslots; j += BLOCK) {
+                if (s_keys[j] != -1) { s_nxt_dyn[j] = __ldcg(rsv_g + j); rsv_g[j] = 0.0; }
+            }
+        }
         __syncthreads();
 
         // ------------------------------------------------------------------ top-k, graph.h:111-126
         const int n_sup = min((long long)sm.n_sup, P.capS);
-        if (tid == 0) { st_support += n_sup; st_maxsup = max(st_maxsup, (unsigned long long)n_sup); }
+        if (tid == 0) {
+            const unsigned long long sup_all = (unsigned long long)n_sup + (SHASH ? (unsigned)sm.n_tab : 0u);
+            st_support += sup_all; st_maxsup = max(st_maxsup, sup_all);
+        }
+        const int n_tslots = SHASH ? P.hslots : 0;
         // pass 0: exponent histogram of the compact reserve values (coalesced; no table access)
         for (int j = tid; j < n_sup; j += BLOCK) {
             const double x = sup_val[j];
+            if (x > 0.0) atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u);
+        }
+        for (int j = tid; j < n_tslots; j += BLOCK) {
+            const double x = s_nxt_dyn[j];
             if (x > 0.0) atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u);
         }
         __syncthreads();
@@ -428,6 +574,14 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
                 }
             }
+            for (int j = tid; j < n_tslots; j += BLOCK) {
+                const double x = s_nxt_dyn[j];
+                if (x > 0.0) {
+                    const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+                    if ((key >> shift) == prefix)
+                        atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
+                }
+            }
             shift = nshift; bits = nbits;
             __syncthreads();
         }
@@ -442,6 +596,22 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 } else if (t == Tkey) {
                     const int pos = atomicAdd(&sm.n_bucket, 1);
                     if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = sup_id[j]; }
+                }
+            }
+        }
+        for (int j = tid; j < n_tslots; j += BLOCK) {
+            const int id = s_keys[j];
+            if (id == -1) continue;
+            const double x = s_nxt_dyn[j];
+            s_keys[j] = -1; s_nxt_dyn[j] = 0.0;   // the table is empty again for the next source
+            if (x > 0.0) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+                const unsigned long long t = key >> shift;
+                if (t > Tkey) {
+                    emit(P, it, src, atomicAdd(&sm.n_out, 1), id, x);
+                } else if (t == Tkey) {
+                    const int pos = atomicAdd(&sm.n_bucket, 1);
+                    if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = id; }
                 }
             }
         }
@@ -463,8 +633,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         __syncthreads();
         // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
         for (int i = sm.n_out + tid; i < P.K; i += BLOCK) emit(P, it, 0, i, 0, 0.0);
+        GP_PHASE(4);
     }
     if (tid == 0) {
+        sm.ph[7] = clock64() - t_begin;
+        for (int i = 0; i < 8; i++) atomicAdd(P.phase + i, (unsigned long long)sm.ph[i]);
         atomicAdd(P.stats + 0, st_edges);
         atomicAdd(P.stats + 1, st_frontier);
         atomicAdd(P.stats + 2, st_support);
@@ -476,6 +649,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     }
 }
 
+#undef GP_PHASE
 #include "gfpush_hash.cuh"
 
 // Hash-tier invariant between sources: every key empty, residues and reserves zero.
@@ -526,6 +700,7 @@ struct gp_graph {
     size_t scratch_bytes = 0;
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
+    int scratch_hslots = 0;
     long long epoch_base = 0;              // sources pushed since the tables were last initialised
     double *d_coef = nullptr;              // [kMaxLevels]
     // [0] queue [1..4] stats [5] hash-tier queue [6] redo count [7] redo queue [8] max support | [16..21] cumulative
@@ -577,7 +752,8 @@ struct Plan {
     long long ctas, capF, capS;
     size_t dyn_smem;
     size_t bytes;
-    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand;
+    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand, off_rsvg;
+    int hslots;  // > 0: MODE 2 (shared-memory hash in front of the slabs)
 };
 
 int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
@@ -615,6 +791,16 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         per_sm = std::min(per_sm, fit);
     }
     long long ctas = (long long)g->num_sms * per_sm;  // scratch is sized for a full grid; small calls launch fewer
+    // MODE 2: the largest power-of-two table {int key, double residue} that fits beside the static shared memory
+    int hslots = 0;
+    if (mode == GP_SCRATCH_HBM && g_push_smem_hash != 0) {
+        const size_t avail = g->smem_optin / (size_t)per_sm;
+        if (avail > stat + 2048) {
+            hslots = 1;
+            while ((size_t)hslots * 2 * 12 + stat + 1024 <= avail) hslots *= 2;
+            if (hslots < 1024) hslots = 0;
+        }
+    }
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
         p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 8), 256);
@@ -624,6 +810,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         p->off_nxt_id = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_sup_id = o; o += align_up((size_t)c * capS * 4, 256);
         p->off_cand = o; o += align_up((size_t)c * capS * 8, 256);
+        p->off_rsvg = o; o += align_up((size_t)c * hslots * 8, 256);
         return o;
     };
     size_t budget = (size_t)g->cfg.max_scratch_bytes;
@@ -635,7 +822,8 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     Plan tmp{};
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
     pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
-    pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : 0;
+    pl->hslots = hslots;
+    pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : (size_t)hslots * 12;
     pl->bytes = bytes_for(ctas, pl);
     GP_REQUIRE(pl->bytes <= budget || ctas == 1, "scratch does not fit the budget");
     return GP_OK;
@@ -644,6 +832,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
 int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream) {
     const bool same = g->scratch && g->scratch_bytes >= pl.bytes && g->scratch_ctas == pl.ctas &&
                       g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode &&
+                      g->scratch_hslots == pl.hslots &&
                       g->epoch_base + S < (1ll << 31) - 2;  // epoch tags are int32: re-initialise before they wrap
     if (same) return GP_OK;
     if (g->scratch && g->scratch_bytes < pl.bytes) {
@@ -661,21 +850,31 @@ int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream
         pl.mode == GP_SCRATCH_HBM ? (int4 *)(base + pl.off_tab) : nullptr,
         pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n);
     GP_CUDA_TRY(cudaGetLastError());
+    if (pl.hslots) GP_CUDA_TRY(cudaMemsetAsync(base + pl.off_rsvg, 0, (size_t)pl.ctas * pl.hslots * 8, stream));
     g->epoch_base = 0;
+    g->scratch_hslots = pl.hslots;
     g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
     return GP_OK;
 }
 
 template <int BLOCK>
 int launch_push(const PushParams &P, const Plan &pl, cudaStream_t stream) {
+    unsigned grid = (unsigned)std::min<long long>(pl.ctas, P.S);
+    if (g_push_max_ctas > 0) grid = std::min(grid, (unsigned)g_push_max_ctas);
     if (pl.mode == GP_SCRATCH_SMEM) {
-        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)pl.dyn_smem));
-        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, 1>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          cudaSharedmemCarveoutMaxShared));
-        gfpush_kernel<BLOCK, true><<<(unsigned)std::min<long long>(pl.ctas, P.S), BLOCK, pl.dyn_smem, stream>>>(P);
+        gfpush_kernel<BLOCK, 1><<<grid, BLOCK, pl.dyn_smem, stream>>>(P);
+    } else if (pl.hslots > 0) {
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)pl.dyn_smem));
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_kernel<BLOCK, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
+        gfpush_kernel<BLOCK, 2><<<grid, BLOCK, pl.dyn_smem, stream>>>(P);
     } else {
-        gfpush_kernel<BLOCK, false><<<(unsigned)std::min<long long>(pl.ctas, P.S), BLOCK, 0, stream>>>(P);
+        gfpush_kernel<BLOCK, 0><<<grid, BLOCK, 0, stream>>>(P);
     }
     GP_CUDA_TRY(cudaGetLastError());
     return GP_OK;
@@ -842,7 +1041,8 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.sup_val = (double *)(base + pl.off_cand);
     P.capF = pl.capF; P.capS = pl.capS;
     P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 16;
-    P.max_support = g->d_ctrl + 8;
+    P.max_support = g->d_ctrl + 8; P.phase = g->d_ctrl + 24;
+    P.rsv_g = (double *)(base + pl.off_rsvg); P.hslots = pl.hslots; P.max_probe = std::max(g_push_smem_probe, 1);
     P.redo = nullptr; P.redo_count = nullptr;
     int launches = 0;
     long long done = 0;  // sources [0, done) are finished by the pilot

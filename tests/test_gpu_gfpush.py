@@ -202,7 +202,8 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
     DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
-                "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0}
+                "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 0,
+                "push_smem_probe": 16, "push_max_ctas": 0}
 
     def __init__(self, **kv):
         self.kv = kv
@@ -218,22 +219,35 @@ class _tuning:
             _lib.set_tuning(k, self.DEFAULTS[k])
 
 
-# (push_hash, push_cluster, push_hash_slots): slabs only / one CTA per source / clusters of 2..16 CTAs per
-# source over DSMEM / a table so small that most sources are handed over to the slabs
-TIERS = [(0, 0, 0), (1, 1, 0), (1, 2, 0), (1, 4, 0), (1, 8, 0), (1, 16, 0), (1, 1, 2048), (1, 4, 2048)]
+# Every tier of HBM-mode GFPush: plain slabs / the shared-memory hash in front of the slabs (default; with a
+# probe limit of 1 and 2 most nodes spill to the slab, so both residencies and their mix are exercised) /
+# the L2 hash tier with one CTA per source, with clusters of 2..16 CTAs per source over DSMEM, and with a table
+# so small that most sources are handed over to the slabs.
+TIERS = {
+    "slab": dict(push_smem_hash=0),
+    "smem": dict(push_smem_hash=1),
+    "smem_probe1": dict(push_smem_hash=1, push_smem_probe=1),
+    "smem_probe2": dict(push_smem_hash=1, push_smem_probe=2),
+    "l2hash_g1": dict(push_hash=1, push_cluster=1, push_pilot=16),
+    "l2hash_g2": dict(push_hash=1, push_cluster=2, push_pilot=16),
+    "l2hash_g4": dict(push_hash=1, push_cluster=4, push_pilot=16),
+    "l2hash_g8": dict(push_hash=1, push_cluster=8, push_pilot=16, push_smem_hash=0),
+    "l2hash_g16": dict(push_hash=1, push_cluster=16, push_pilot=16),
+    "l2hash_g1_tiny": dict(push_hash=1, push_cluster=1, push_hash_slots=2048, push_pilot=16),
+    "l2hash_g4_tiny": dict(push_hash=1, push_cluster=4, push_hash_slots=2048, push_pilot=16, push_smem_hash=0),
+}
 
 
-@pytest.mark.parametrize("tier", TIERS)
-def test_gfpush_hash_tier_clusters_and_handover(tier):
-    """The L2-resident hash tier at every cluster size, the direct-addressed slabs, and the hand-over from
-    one to the other must all give the oracle's rows and the oracle's work counters."""
+@pytest.mark.parametrize("tier", sorted(TIERS))
+def test_gfpush_tiers_give_the_oracle_rows_and_counters(tier):
+    """Every tier, and the hand-over between tiers, must give the oracle's rows and the oracle's work counters."""
     from grandplus_b200 import synth
-    use_hash, cluster, slots = tier
+    kv = TIERS[tier]
     indptr, indices = synth.powerlaw_csr(60_000, 700_000, seed=5)
     indptr, indices = indptr.numpy(), indices.numpy()
     src = synth.sources(60_000, 400, seed=4).numpy()
     coef = og.coef_for("ppr", 6, 0.05)
-    with _tuning(push_hash=use_hash, push_cluster=cluster, push_hash_slots=slots, push_pilot=16):
+    with _tuning(**kv):
         g = _graph(indptr, indices, scratch_mode=HBM)
         g.cumulative_stats(reset=True)
         row, col, val = _run(g, src, coef, 1e-5, 32)
@@ -248,9 +262,9 @@ def test_gfpush_hash_tier_clusters_and_handover(tier):
     assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
     assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
     assert st["sources"] == len(src)
-    if not use_hash:
+    if not kv.get("push_hash"):
         assert st["hash_sources"] == 0 and st["hash_fallbacks"] == 0
-    elif slots:
+    elif kv.get("push_hash_slots"):
         assert st["hash_fallbacks"] > 0 and st["hash_sources"] + st["hash_fallbacks"] == len(src) - 16
     else:
         assert st["hash_sources"] > 0.5 * len(src)
@@ -259,6 +273,20 @@ def test_gfpush_hash_tier_clusters_and_handover(tier):
     for (ac, av), (bc, bv) in zip(og.rows_as_sets(col, val, 32), og.rows_as_sets(col2, val2, 32)):
         if np.array_equal(ac, bc):
             np.testing.assert_allclose(av, bv, rtol=1e-12)
+
+
+@pytest.mark.parametrize("probe", [1, 3, 16])
+@pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("pubmed", "ppr"), ("citeseer", "single")])
+def test_gfpush_smem_hash_matches_reference_golden(name, mode, probe):
+    """Real graphs through the shared-memory hash tier in HBM mode (Cora's ppr support is the whole component)."""
+    indptr, indices = load_graph(name)
+    z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
+    K, rmax = int(z["K"]), float(z["rmax"])
+    with _tuning(push_smem_hash=1, push_smem_probe=probe):
+        g = _graph(indptr, indices, scratch_mode=HBM)
+        row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
+    worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
+    assert worst < 1e-11, worst
 
 
 @pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("citeseer", "avg"), ("pubmed", "ppr"), ("pubmed", "single")])

@@ -17,7 +17,7 @@ from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
 DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
-            "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0}
+            "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 0, "push_smem_probe": 16, "push_max_ctas": 0}
 
 
 def main():
@@ -61,8 +61,10 @@ def main():
               f"scratch={st['scratch_bytes'] / 1e6:.0f}MB", flush=True)
         ph = graph.phase_cycles(reset=True)
         if ph["resident"]:
-            print("    phases (% of leader-CTA residency): " +
-                  " ".join(f"{k}={100.0 * v / ph['resident']:.1f}" for k, v in ph.items() if k != "resident"), flush=True)
+            names = ph.keys() if st["hash_sources"] else ("fetch", "expand", "settle", "-", "topk", "wide_expand", "wide_settle")
+            us = ph["resident"] / 1965.0 / max(st["sources"], 1)
+            print(f"    {us:.0f} us of CTA time per source; % by phase: " +
+                  " ".join(f"{n}={100.0 * v / ph['resident']:.1f}" for n, v in zip(names, ph.values()) if n != "-"), flush=True)
     for k, v in DEFAULTS.items():
         _lib.set_tuning(k, v)
 
