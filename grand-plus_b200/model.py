@@ -113,12 +113,18 @@ def dropnode_mask(n_entries: int, n_aug: int, p: float, seed: int, offset: int, 
 
 
 def _launch_fwd(table, F_cols, ld_table, row_ptr, slot_rows, slot_K, nbr, score, B, n_entries, p, training, n_aug,
-                seed, offset, mask_in, want_mask, eps, want_denom):
+                seed, offset, mask_in, want_mask, eps, want_denom, out=None):
     lib = _lib.load()
     dev = table.device
     # rows padded to a 16-byte multiple so the kernel can use 128-bit stores; callers get the [.., :F] view
     ld_out = (int(F_cols) + 3) // 4 * 4
-    out = torch.empty((n_aug, B, ld_out), dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((n_aug, B, ld_out), dtype=torch.float32, device=dev)
+    else:   # caller-provided [n_aug, B, ld] fp32 buffer (may be a row range of a larger table)
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape[-1] % 4 == 0
+        assert out.numel() == n_aug * B * out.shape[-1] and out.shape[-1] >= ld_out
+        ld_out = int(out.shape[-1])
+        out = out.view(n_aug, B, ld_out)
     mask_out = torch.empty((n_aug, n_entries), dtype=torch.uint8, device=dev) if want_mask else None
     denom = torch.empty((n_aug, B), dtype=torch.float32, device=dev) if want_denom else None
     a = _lib.AggregateArgs()

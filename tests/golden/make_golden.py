@@ -209,11 +209,55 @@ def gen_aggregate():
     np.savez_compressed(os.path.join(HERE, "emb.npz"), **out)
 
 
+def gen_predict():
+    """The matrix the reference's own ``predict`` (model.py:181-224) hands to the MLP, captured by
+    intercepting ``get_local_logits``; real Cora / Citeseer graphs (+I), random 12-column features."""
+    import torch
+    _install_scatter_standin()
+    pre = types.ModuleType("precompute")
+    pre.propagation = og.load_reference()
+    sys.modules.setdefault("precompute", pre)
+    sys.modules.setdefault("precompute.propagation", pre.propagation)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import model as ref_model
+    captured = []
+
+    def fake_logits(mlp, feat, batch_size=10000):
+        captured.append(np.array(feat))
+        return np.zeros((feat.shape[0], 2), dtype=np.float32)
+
+    ref_model.get_local_logits = fake_logits
+    rng = np.random.default_rng(11)
+    out = {}
+    for name in ("cora", "citeseer"):
+        z = np.load(os.path.join(HERE, f"graph_{name}.npz"))
+        n = len(z["indptr"]) - 1
+        adj = sp.csr_matrix((np.ones(len(z["indices"])), z["indices"], z["indptr"]), shape=(n, n))
+        X = rng.standard_normal((n, 12)).astype(np.float32)
+        out[f"{name}/X"] = X
+        for mode, order, alpha in (("ppr", 6, 0.2), ("avg", 4, 0.2), ("single", 2, 0.2)):
+            args = types.SimpleNamespace(order=order, alpha=alpha)
+            net = types.SimpleNamespace(eval=lambda: None, mlp=None)
+            captured.clear()
+            ref_model.predict(args, adj, X.copy(), net, np.arange(4), torch.zeros(n, dtype=torch.long), mode=mode)
+            tag = f"{name}/{mode}_o{order}_a{alpha:g}"
+            out[f"{tag}/order"] = np.int32(order)
+            out[f"{tag}/alpha"] = np.float64(alpha)
+            out[f"{tag}/feat"] = captured[0].astype(np.float32)
+            print(f"predict {tag}: feat {captured[0].shape} {captured[0].dtype}")
+    np.savez_compressed(os.path.join(HERE, "predict.npz"), **out)
+
+
 if __name__ == "__main__":
     if not og.reference_available():
         raise SystemExit("build the reference first: make -C oracle ref")
+    if "--only-predict" in sys.argv:
+        gen_predict()
+        raise SystemExit(0)
     gen_gfpush()
     gen_aggregate()
+    gen_predict()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f"{f}: {os.path.getsize(os.path.join(HERE, f))/1024:.1f} KiB")

@@ -141,3 +141,22 @@ def test_batch_slice_matches_scipy_contract():
     s, nb, sc = oa.batch_slice(adj, batch)
     assert s[0] == 0 and s[-1] == 9 and np.all(np.diff(s) >= 0)
     assert sc.dtype == np.float32 and len(sc) == len(nb)
+
+
+@pytest.mark.parametrize("name", ["cora", "citeseer"])
+def test_predict_oracle_matches_reference_golden(name):
+    """oracle.predict.propagate_exact against what the reference's own predict() hands to its MLP."""
+    import scipy.sparse as sp
+    from oracle import predict as op
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "predict.npz"))
+    g = np.load(os.path.join(GOLDEN, f"graph_{name}.npz"))
+    n = len(g["indptr"]) - 1
+    adj = sp.csr_matrix((np.ones(len(g["indices"])), g["indices"], g["indptr"]), shape=(n, n))
+    X = z[f"{name}/X"]
+    tags = sorted({k.split("/")[1] for k in z.files if k.startswith(name + "/") and k.count("/") == 2})
+    assert len(tags) == 3
+    for tag in tags:
+        mode = tag.split("_")[0]
+        got = op.propagate_exact(adj, X.copy(), int(z[f"{name}/{tag}/order"]), float(z[f"{name}/{tag}/alpha"]), mode)
+        np.testing.assert_array_equal(got.astype(np.float32), z[f"{name}/{tag}/feat"])   # same arithmetic: bit-exact

@@ -26,6 +26,14 @@ def main():
     steps = int(os.environ.get("SWEEP_STEPS", "4"))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    if os.environ.get("SWEEP_L2_GRAN"):   # cudaLimitMaxL2FetchGranularity = 0x05
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        torch.zeros(1, device=dev)
+        rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["SWEEP_L2_GRAN"])))
+        val = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+        print("L2 fetch granularity set rc", rc, "now", val.value, flush=True)
     w = bench.WORKLOADS[name]
     S = int(os.environ.get("SWEEP_SOURCES", w["S"]))
     indptr, indices, n = bench.build_workload(name, dev)
