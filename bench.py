@@ -45,6 +45,10 @@ WORKLOADS = {
                    S=16384),
     "amazon2m": dict(config=3, n=2_449_029, draws=61_859_140, F=100, mode="ppr", order=6, alpha=0.2, rmax=1e-6,
                      K=64, S=16384),
+    # MAG-Scholar-C shape (scripts/run_mag.sh:7); F = the hidden width: on the model_mag path the table the
+    # aggregation reads is the [N, hidden] output of MLP.emb, not the 2.78M-column sparse attribute matrix
+    "mag": dict(config=4, n=10_541_560, draws=265_219_994, F=64, mode="ppr", order=10, alpha=0.2, rmax=1e-5, K=32,
+                S=16384),
     "small": dict(config=-1, n=50_000, draws=600_000, F=64, mode="ppr", order=6, alpha=0.05, rmax=1e-5, K=32, S=2048),
 }
 DROPNODE_P = 0.5   # run_model.py:56 default
@@ -89,23 +93,35 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
+        self.samples = []      # (arrival time, csv line)
         self.proc = None
+        self.windows = []      # [t0, t1] of the timed regions
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.samples.append(line.strip())
+                self.samples.append((time.time(), line.strip()))
         except Exception:
             pass
 
+    def wait_first_sample(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while not self.samples and time.time() < t_end:
+            time.sleep(0.01)
+
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
+        time.sleep(0.06)   # let the last periodic sample arrive
         if self.proc:
             self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for s in self.samples:
+        for t, s in self.samples:
+            if not any(t0 <= t <= t1 + 0.05 for t0, t1 in self.windows):
+                continue
             f = [x.strip() for x in s.split(",")]
             if len(f) < 9:
                 continue
@@ -117,7 +133,8 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "window": "device-timed steps + end-to-end steps (both under load)"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -198,13 +215,15 @@ def run_ours(args):
     # ------------------------------------------------------------------ device-resident timing
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     sampler = ClockSampler(local)
+    sampler.start()
+    sampler.wait_first_sample()
     checks = []
     for i in range(total):
         if i == args.warmup:
             torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
             graph.cumulative_stats(reset=True)
-            sampler.start()
             t0 = time.perf_counter()
+            w0 = time.time()
         timed = i >= args.warmup
         if timed:
             ev[i - args.warmup][0].record()
@@ -218,7 +237,7 @@ def run_ours(args):
         del out, col, val32, _row, _val
     torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    sampler.mark(w0, time.time())
     t_push = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
     t_agg = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
     t_dev = ev[0][0].elapsed_time(ev[-1][2]) / 1e3   # CUDA events on the launching stream, first to last timed launch
@@ -267,6 +286,7 @@ def run_ours(args):
         if i == 2:
             torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
+            w0 = time.time()
         h_node.copy_(host_batches[(args.warmup + i) % total])
         graph.gfpush_omp(h_node.numpy(), h_row.numpy(), h_col.numpy(), h_val.numpy(), coef, w["rmax"], K)
         d_col = h_col.to(dev, non_blocking=True).reshape(S, K)              # model.py:314-316: the batch's
@@ -275,6 +295,8 @@ def run_ours(args):
         chk = float(out.sum().item())                                       # D2H read of the step's result
     torch.cuda.synchronize(); barrier()
     e2e_time = gd.max_over_ranks(time.perf_counter() - t0, device=dev)
+    sampler.mark(w0, time.time())
+    clocks = sampler.stop()
     e2e = {"value": S * e2e_steps * world / e2e_time, "unit": UNIT, "h2d_bytes_per_step": S * 4 + S * K * 12,
            "d2h_bytes_per_step": S * K * 16 + 4, "steps": e2e_steps, "ms_per_step": e2e_time / e2e_steps * 1e3,
            "api": "Graph.gfpush_omp(host arrays) + aggregate_slots(H2D col/score) + checksum D2H", "checksum": chk}
@@ -293,7 +315,7 @@ def run_ours(args):
                    "scratch_mode": {1: "smem", 2: "hbm"}.get(stats["scratch_mode"]), "persistent_ctas": stats["ctas"]},
         "roofline": dominant, "roofline_gfpush": roof_push, "roofline_aggregate": roof_agg,
         "aggregation_gb_per_s": roof_agg["achieved"],
-        "e2e": e2e, "gpu_launches": 2 * args.steps, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": (int(stats.get("kernel_launches") or 1) + 1) * args.steps, "clocks": clocks,
         "setup_s": t_setup, "impl": "ours", "wall_ms_per_step": wall / args.steps * 1e3,
     }
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -227,16 +227,40 @@ __device__ __forceinline__ void emit(const Params &P, long long it, int src, int
     if (P.out_val32) P.out_val32[o] = (float)v;
 }
 
+// L2 eviction-priority hints (experiment): the slab sectors touched by a level's expand are read again by its
+// settle; keep them (evict_last) and let the streams (CSR indices, lists) go first (evict_first / .cs).
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double atom_add_f64_hint(double *p, double x, unsigned long long pol) {
+    double old;
+    asm volatile("atom.global.add.L2::cache_hint.f64 %0, [%1], %2, %3;" : "=d"(old) : "l"(p), "d"(x), "l"(pol) : "memory");
+    return old;
+}
+__device__ __forceinline__ int4 ldcg_int4_hint(const void *p, unsigned long long pol) {
+    int4 r;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_int4_hint(void *p, int4 v, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1, %2, %3, %4}, %5;"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
 // Per-CTA view of the next-residue table.
 template <bool SMEM_NXT>
 struct Tables {
     Slot *tab;      // HBM mode
     int2 *meta;     // SMEM mode
     double *s_nxt;  // SMEM mode
+    unsigned long long pol;  // L2 evict_last policy for the slab sectors
     // next[v] += x; true when v had no residue yet (first touch at this level)
     __device__ __forceinline__ bool add_next(int v, double x) const {
-        double *p = SMEM_NXT ? (s_nxt + v) : &tab[v].nxt;
-        return atomicAdd(p, x) == 0.0;  // graph.h:98
+        if (SMEM_NXT) return atomicAdd(s_nxt + v, x) == 0.0;
+        return atom_add_f64_hint(&tab[v].nxt, x, pol) == 0.0;  // graph.h:98
     }
     // Takes next[v] (leaving 0).  pos >= 0: v already has a reserve entry at that position.
     __device__ __forceinline__ double take(int v, int epoch, int &pos) const {
@@ -249,7 +273,7 @@ struct Tables {
         } else {
             const double4 *unused = nullptr; (void)unused;
             // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
-            const int4 raw = __ldcg(reinterpret_cast<const int4 *>(tab + v));
+            const int4 raw = ldcg_int4_hint(tab + v, pol);
             pos = (raw.z == epoch) ? raw.w : -1;
             return __hiloint2double(raw.y, raw.x);
         }
@@ -257,7 +281,7 @@ struct Tables {
     // Clears next[v] and records (epoch, pos): one 16-byte write (HBM) / 8-byte write (SMEM).
     __device__ __forceinline__ void put(int v, int epoch, int pos, bool changed) const {
         if (SMEM_NXT) { if (changed) meta[v] = make_int2(epoch, pos); }
-        else *reinterpret_cast<int4 *>(tab + v) = make_int4(0, 0, epoch, pos);
+        else st_int4_hint(tab + v, make_int4(0, 0, epoch, pos), pol);
     }
 };
 
@@ -285,6 +309,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     T.tab = SMEM_NXT ? nullptr : P.tab + cta * (long long)P.n;
     T.meta = SMEM_NXT ? P.meta + cta * (long long)P.n : nullptr;
     T.s_nxt = s_nxt_dyn;
+    T.pol = l2_policy_evict_last();
     int *push_start = P.push_start + cta * P.capF;
     int *push_deg = P.push_deg + cta * P.capF;
     double *push_val = P.push_val + cta * P.capF;
@@ -392,7 +417,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                             const int t = owner_of_edge<BLOCK>(sm.off, e);
                             const int st = sm.start[t];
                             add[q] = sm.val[t];
-                            if (st >= 0) v[q] = __ldg(P.indices + st + (e - sm.off[t]));  // graph.h:96-97
+                            if (st >= 0) v[q] = __ldcs(P.indices + st + (e - sm.off[t]));  // graph.h:96-97 (streaming: evict first)
                         }
                     }
                     bool fresh[kEdgeUnroll];
