@@ -267,7 +267,13 @@ def run_ours(args):
                  "algorithmic_bytes_per_launch": push_bytes / args.steps,
                  "hash_tier_sources": stats.get("hash_sources"), "hash_tier_fallbacks": stats.get("hash_fallbacks"),
                  "frontier_per_source": stats["frontier_total"] / (S * args.steps),
-                 "support_per_source": stats["support_total"] / (S * args.steps)}
+                 "support_per_source": stats["support_total"] / (S * args.steps),
+                 # the kernel's binding roof is random 8-16 byte read-modify-writes, not streaming bandwidth:
+                 # fp64 atomics on a footprint beyond L2 run at 20.9 G/s on this part (tools/microbench/random_access.cu,
+                 # profiles/r01_random_access_microbench.txt); one pushed edge = one such atomic
+                 "random_access": {"achieved_edge_atomics_per_s": stats["edges_pushed"] / t_push, "roof_atomics_per_s": 20.9e9,
+                                   "frac": stats["edges_pushed"] / t_push / 20.9e9,
+                                   "roof_source": "profiles/r01_random_access_microbench.txt (atomicAdd f64, 17-34 GB footprint)"}}
     roof_agg = {"kernel": "aggregate_fwd_kernel", "bound": "hbm", "achieved": agg_bytes / t_agg / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": agg_bytes / t_agg / 1e9 / peak,
                 "traffic": load_traffic(args.workload, "aggregate_fwd_kernel"), "peak_source": peak_src,
@@ -318,6 +324,8 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": (int(stats.get("kernel_launches") or 1) + 1) * args.steps, "clocks": clocks,
         "setup_s": t_setup, "impl": "ours", "wall_ms_per_step": wall / args.steps * 1e3,
     }
+    if rank == 0 and world == 1 and args.workload != "pubmed":
+        line["config1_pubmed"] = pubmed_side_measurement(dev)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.workload, indptr.cpu().numpy(), indices.cpu().numpy(), n,
                                             budget_s=args.cpu_budget)
@@ -326,6 +334,45 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         emit_line(line)
+
+
+def pubmed_side_measurement(dev, steps=5):
+    """BASELINE configs[1] -- Pubmed, ppr/avg/single (scripts/run_pubmed.sh:7,11,15) on one B200 -- reported
+    beside the headline workload.  The Pubmed graph and X are L2-resident, so L2 is flushed (a 512 MB write)
+    between timed steps.  All 19 717 nodes are the sources of every step."""
+    import torch
+    from grandplus_b200 import model as gm
+    from grandplus_b200 import synth
+    from grandplus_b200.precompute import propagation
+    z = np.load(os.path.join(ROOT, "tests", "golden", "graph_pubmed.npz"))
+    indptr = torch.from_numpy(z["indptr"]).to(dev)
+    indices = torch.from_numpy(z["indices"]).to(dev)
+    n = int(indptr.numel() - 1)
+    graph = propagation.Graph.from_device_csr(indptr, indices)
+    feats = gm.DeviceFeatures(synth.features(n, 500, seed=1, device=dev))
+    src = synth.sources(n, n, seed=1, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    out = {"nodes": n, "csr_nnz": int(indices.numel()), "sources_per_step": n, "top_k": 16, "rmax": 1e-5,
+           "l2": "flushed between steps (512 MB write)", "steps": steps}
+    for mode, order, alpha in (("ppr", 6, 0.5), ("avg", 4, 0.2), ("single", 2, 0.2)):
+        coef = coef_for(mode, order, alpha)
+        t_push = t_agg = 0.0
+        for i in range(3 + steps):
+            flush.fill_(i & 0xFF)
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            _r, col, _v, val32 = graph.gfpush_device(src, coef, 1e-5, 16, want_fp32=True)
+            e[1].record()
+            res = gm.aggregate_slots(feats, col, val32, None, DROPNODE_P, True, n_aug=N_AUG, seed=1234, offset=i)
+            e[2].record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                t_push += e[0].elapsed_time(e[1]) / 1e3
+                t_agg += e[1].elapsed_time(e[2]) / 1e3
+            del res, col, val32, _r, _v
+        out[mode] = {"order": order, "alpha": alpha, "gfpush_rows_per_s": n * steps / t_push,
+                     "aggregate_rows_per_s": n * steps / t_agg, "rows_per_s": n * steps / (t_push + t_agg)}
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

@@ -330,6 +330,35 @@ class PiMatrix:
         _row, col, _val, val32 = graph.gfpush_device(nid, coef, rmax, K, want_fp32=True)
         return cls(nid, col, val32, graph.num_nodes)
 
+    # -- cache on disk: the reference recomputes GFPush for every (seed1, seed2) run ---------
+    @staticmethod
+    def cache_key(indptr, indices, node_idx, coef, rmax, K) -> str:
+        """Hash of everything Pi depends on (graph, sources, coef, rmax, K)."""
+        import hashlib
+        import numpy as np
+        h = hashlib.sha256()
+        for a, dt in ((indptr, np.int32), (indices, np.int32), (node_idx, np.int64), (coef, np.float64)):
+            a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+            h.update(np.ascontiguousarray(a.astype(dt, copy=False)).tobytes())
+        h.update(repr((float(rmax), int(K))).encode())
+        return h.hexdigest()[:32]
+
+    def save(self, path: str, key: str = "") -> None:
+        import numpy as np
+        np.savez(path, node_idx=self.node_idx.cpu().numpy(), col=self.col.cpu().numpy(), val=self.val.cpu().numpy(),
+                 n_nodes=np.int64(self.row_of_node.numel()), key=np.array(key))
+
+    @classmethod
+    def load(cls, path: str, device=None, key: str = None):
+        """The saved matrix, or None when ``key`` is given and does not match the file's."""
+        import numpy as np
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        if key is not None and str(z["key"]) != key:
+            return None
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return cls(torch.from_numpy(z["node_idx"]).to(device), torch.from_numpy(z["col"]).to(device),
+                   torch.from_numpy(z["val"]).to(device), int(z["n_nodes"]))
+
     def slot_rows(self, batch_nodes) -> torch.Tensor:
         b = torch.as_tensor(batch_nodes).to(device=self.col.device, dtype=torch.int64)
         rows = self.row_of_node[b]

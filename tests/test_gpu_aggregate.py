@@ -219,3 +219,28 @@ def test_rejects_cpu_tensors_and_unsorted_index():
     with pytest.raises(IndexError):
         gm.random_prop_fused(gm.DeviceFeatures(np.zeros((5, 4), np.float32)), torch.tensor([0, 7]).cuda(),
                              torch.ones(2).cuda(), torch.tensor([0, 0]).cuda(), 0.5)
+
+
+def test_pimatrix_disk_cache_roundtrip(tmp_path):
+    """Pi saved and reloaded aggregates to the same rows; a different key is a cache miss."""
+    import torch
+    from grandplus_b200 import model as gm
+    from grandplus_b200.precompute import propagation
+    from tests.helpers import load_graph
+    from oracle import gfpush as og
+    indptr, indices = load_graph("cora")
+    n = indptr.shape[0] - 1
+    coef = og.coef_for("ppr", 6, 0.2)
+    src = np.arange(0, n, 5, dtype=np.int32)
+    g = propagation.Graph(indptr, indices, 0)
+    pi = gm.PiMatrix.from_graph(g, src, coef, 1e-6, 16)
+    key = gm.PiMatrix.cache_key(indptr, indices, src, coef, 1e-6, 16)
+    assert key != gm.PiMatrix.cache_key(indptr, indices, src, coef, 1e-5, 16)
+    path = str(tmp_path / "pi_cache")
+    pi.save(path, key)
+    assert gm.PiMatrix.load(path, key="something else") is None
+    pi2 = gm.PiMatrix.load(path, key=key)
+    X = gm.DeviceFeatures(np.random.default_rng(0).standard_normal((n, 33)).astype(np.float32))
+    a = pi.aggregate(X, src[:100], 0.5, training=True, n_aug=2, seed=3, offset=4)
+    b = pi2.aggregate(X, src[:100], 0.5, training=True, n_aug=2, seed=3, offset=4)
+    assert torch.equal(a, b)
