@@ -32,9 +32,10 @@
 #include <vector>
 
 // tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
-int g_push_smem_hash = 0;     // "push_smem_hash": 1 = shared-memory hash table in front of the slabs (HBM mode, MODE 2 kernel);
-                              // opt-in: measured 10-25 % slower than the plain slabs (profiles/r01_hash_tier.md)
-int g_push_smem_probe = 16;   // "push_smem_probe": probes before a node is sent to the slab
+int g_push_smem_hash = 1;     // "push_smem_hash": shared-memory residue table in front of the slabs (HBM mode, MODE 2 kernel):
+                              // 0 off, 1 auto (on when the expected support is of the order of the table), 2 always on
+int g_push_debug = 0;
+int g_push_smem_probe = 4;    // "push_smem_probe": probes before a node is sent to the slab
 int g_push_hash = 0;          // "push_hash": 1 = route HBM-mode sources through the L2-resident hash tier first
                               // (opt-in: measured slower than the slabs on every BASELINE shape, profiles/r01_hash_tier.md)
 int g_push_cluster = 0;       // "push_cluster": CTAs per source (1,2,4,8,16), 0 = from the pilot statistics
@@ -68,6 +69,7 @@ struct __align__(16) Slot {
 
 struct PushParams {
     const int *indptr;
+    const int2 *node_rec;  // [n] {indptr[v], degree}: the pair settle needs, as ONE aligned 8-byte load
     const int *indices;
     int n;
     const int *node_idx;
@@ -99,10 +101,13 @@ struct PushParams {
     const unsigned long long *redo_count;
     unsigned long long *max_support;  // largest reserve support of any source of this launch (pilot statistics)
     unsigned long long *phase;        // SM cycles per phase, summed over CTAs (see gp_gfpush_phase_cycles)
-    // MODE 2 (shared-memory hash in front of the slabs): reserve of the nodes resident in shared memory,
-    double *rsv_g;     // [ctas][hslots], parallel to the shared-memory table slots (coalesced, L2-resident)
-    int hslots;        // power of two
-    int max_probe;     // a node that finds no slot within this many probes lives on the slab for this source
+    // MODE 2 (per-level residue table in shared memory in front of the slabs)
+    int *log_id;       // [ctas][capLog]  reserve log: one (node, coef * residue) entry per settled table resident,
+    double *log_val;   // [ctas][capLog]  appended coalesced, merged in shared memory before the top-k
+    long long capLog;
+    int hslots;        // table slots, power of two
+    int max_probe;     // a node that finds no slot within this many probes goes to the slab for this level
+    int debug;         // experiments only
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -118,7 +123,11 @@ struct PushSmem {
     int bid[kBucketCap];
     long long it;
     int n_push, n_nxt, n_sup, n_out, n_bucket;
-    int n_tab;   // MODE 2: nodes resident in the shared-memory table
+    int n_log;     // MODE 2: entries in the reserve log
+    int n_tfront;  // MODE 2: table residents in the current frontier
+    int n_tab;     // MODE 2: distinct nodes in the shared-memory table after the merge
+    int table_on;  // MODE 2: this CTA currently uses the table (off when most edges spill: supports far beyond it)
+    unsigned spill_edges, all_edges, trial;
     long long ph[8], t_prev, wide_expand, wide_settle;   // thread 0: cycles per phase (gp_gfpush_phase_cycles)
     unsigned wide_E;
     int sel_bin, sel_above, sel_inbin;
@@ -286,12 +295,18 @@ struct Tables {
 };
 
 // MODE 0: direct-addressed slabs in HBM.  MODE 1: dense next-residue array in shared memory (small graphs).
-// MODE 2: open-addressed {key, next residue} table in SHARED MEMORY in front of the slabs: a node lives in the
-//   table for the whole source if it finds a slot within max_probe probes when it is first touched, otherwise on
-//   the slab (both decisions are stable: entries are never removed while the source is live).  Table hits cost
-//   shared-memory atomics (measured 1.18 find-or-claim + fp64 add per clock per SM,
-//   profiles/r01_smem_atomics_microbench.txt) instead of a DRAM round trip, settle walks the table instead of
-//   a list, and the reserve of table residents is a global array parallel to the slots (coalesced).
+// MODE 2: an open-addressed {key, next residue} table in SHARED MEMORY in front of the slabs.  A node that finds a
+//   slot within max_probe probes when the source first touches it lives in the table until the source is done,
+//   every other node lives on the slab (both decisions are stable: entries are never removed while a source is live).
+//   expand: table residents cost a probe and a shared-memory atomic (measured 0.6 edges/clk/SM incl. probing at a
+//           table load of 0.8, profiles/r01_smem_hash_microbench.txt) instead of a DRAM round trip;
+//   settle: the table is walked (16 slots per thread, warps skip empty stretches); a resident's coef * residue is
+//           APPENDED to a reserve log as (slot, value) -- coalesced, no read-modify-write in global memory; the only
+//           scattered access left per node is its indptr pair;
+//   after the last level the log is summed into the (then all-zero) residue array by slot, the top-k reads shared
+//   memory, and the slab residents' reserve is in the support arrays exactly as in MODE 0.
+//   A CTA whose sources spill most of their edges (supports far beyond the table) switches the table off and
+//   re-tries 32 sources later.
 template <int BLOCK, int MODE>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams P) {
     constexpr bool SMEM_NXT = MODE == 1;
@@ -300,7 +315,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     extern __shared__ double s_nxt_dyn[];
     int *s_keys = reinterpret_cast<int *>(s_nxt_dyn + (SHASH ? P.hslots : 0));  // SHASH: [hslots] after the residues
     const unsigned hmask = (unsigned)(P.hslots - 1);
-    double *rsv_g = SHASH ? P.rsv_g + (long long)blockIdx.x * P.hslots : nullptr;
+    int *log_id = SHASH ? P.log_id + (long long)blockIdx.x * P.capLog : nullptr;
+    double *log_val = SHASH ? P.log_val + (long long)blockIdx.x * P.capLog : nullptr;
 
     const int tid = threadIdx.x;
     const int lane = gp_lane();
@@ -323,10 +339,13 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     }
     if (SHASH) {
         for (int i = tid; i < P.hslots; i += BLOCK) { s_nxt_dyn[i] = 0.0; s_keys[i] = -1; }
+        if (tid == 0) { sm.table_on = 1; sm.trial = 0; }
     }
-    // SHASH: slot of node v in the shared-memory table (claiming one if v is new), or -1 = v lives on the slab
+    bool table_on = false;   // this level / merge uses the table
+    // SHASH: slot of node v in the shared-memory table (claiming one if v is new), or -1 = no slot within max_probe
     auto s_find = [&](int v, bool &claimed) -> int {
         claimed = false;
+        if (!table_on) return -1;
         unsigned h = ((unsigned)v * 2654435761u) >> 7 & hmask;
         for (int probe = 0; probe < P.max_probe; probe++, h = (h + 1) & hmask) {
             int k = s_keys[h];
@@ -347,7 +366,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         __syncthreads();
         if (tid == 0) {
             sm.it = (long long)atomicAdd(P.queue, 1ull);
-            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0; sm.n_tab = 0;
+            sm.n_push = 0; sm.n_nxt = 0; sm.n_sup = 0; sm.n_out = 0; sm.n_bucket = 0; sm.n_tab = 0; sm.n_log = 0;
+            sm.spill_edges = 0; sm.all_edges = 0;
         }
         __syncthreads();
         long long it = sm.it;
@@ -362,13 +382,14 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             continue;
         }
         const int epoch = P.epoch_base + (int)it + 1;
+        table_on = SHASH && sm.table_on != 0;   // fixed for the whole source: residency must not change between levels
         // level 0: residue = {src: 1}, reserve = {src: 0} (graph.h:80-81); settle it right away
         if (tid == 0) {
             st_sources++; st_frontier++;
-            if (SHASH) {   // the table is empty: the source claims its home slot
+            if (SHASH && sm.table_on) {   // the table is empty: the source claims its home slot; reserve[src] = coef[0]
                 bool claimed;
                 const int h = s_find(src, claimed);
-                rsv_g[h] = P.coef[0]; sm.n_tab = 1;
+                log_id[0] = h; log_val[0] = P.coef[0]; sm.n_log = 1; sm.n_tab = 1;
             } else {
                 T.put(src, epoch, 0, true);
                 sup_id[0] = src; sup_val[0] = P.coef[0]; sm.n_sup = 1;
@@ -389,8 +410,9 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             // Only nodes that passed r >= rmax*deg are in the push list.  A tile of BLOCK of them is
             // prefix-summed by degree and the tile's edges are dealt to threads by rank.
             const int n_push = sm.n_push;
-            int n_claims = 0;
+            int n_spill = 0, n_claims = 0;
             unsigned lvl_E = 0;
+
             for (int base = 0; base < n_push; base += BLOCK) {
                 const int j = base + tid;
                 unsigned d_push = 0;
@@ -421,7 +443,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         }
                     }
                     bool fresh[kEdgeUnroll];
-                    int entry[kEdgeUnroll];   // what the frontier list stores: node id (slab resident) or ~slot (table resident)
                     if (SHASH) {
                         int h[kEdgeUnroll];
 #pragma unroll
@@ -433,28 +454,30 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         }
 #pragma unroll
                         for (int q = 0; q < kEdgeUnroll; q++) {
-                            fresh[q] = false; entry[q] = v[q];
+                            fresh[q] = false;
                             if (ok[q]) {
-                                if (h[q] >= 0) { fresh[q] = atomicAdd(s_nxt_dyn + h[q], add[q]) == 0.0; entry[q] = ~h[q]; }
-                                else fresh[q] = T.add_next(v[q], add[q]);
+                                if (h[q] >= 0) { if (P.debug & 1) s_nxt_dyn[h[q]] += add[q]; else atomicAdd(s_nxt_dyn + h[q], add[q]); }      // table: settle walks the slots
+                                else { fresh[q] = T.add_next(v[q], add[q]); n_spill++; }  // slab: first touch -> list
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < kEdgeUnroll; q++) { fresh[q] = ok[q] && T.add_next(v[q], add[q]); entry[q] = v[q]; }
+                        for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next(v[q], add[q]);
                     }
                     long long lpos[kEdgeUnroll];
-                    warp_append_multi<kEdgeUnroll>(fresh, P.capF, &sm.n_nxt, err, lpos);
+                    warp_append_multi<kEdgeUnroll>(fresh, P.capS, &sm.n_nxt, err, lpos);
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++)
-                        if (lpos[q] >= 0) nxt_id[lpos[q]] = entry[q];
+                        if (lpos[q] >= 0) nxt_id[lpos[q]] = v[q];
                 }
                 __syncthreads();
             }
             if (SHASH) {
+                n_spill = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_spill);
+                if (lane == 0 && n_spill) atomicAdd(&sm.spill_edges, (unsigned)n_spill);
                 n_claims = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_claims);
                 if (lane == 0 && n_claims) atomicAdd(&sm.n_tab, n_claims);
-                n_claims = 0;
+                if (tid == 0) sm.all_edges += lvl_E;
             }
             if (n_push == 0) __syncthreads();
             long long t_e = 0;
@@ -467,8 +490,61 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const int next_level = level + 1;
             const bool will_push = next_level < P.L - 1;
             const double c = P.coef[next_level];
-            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
+            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; sm.n_tfront = 0; }
             __syncthreads();
+            if (SHASH && table_on) {
+                // table residents: walk the residues; a warp whose stretch holds none moves on at once
+                unsigned cnt = 0;
+                for (int base = 0; base < P.hslots; base += BLOCK * kSettleUnroll) {
+                    double x[kSettleUnroll];
+                    bool ok[kSettleUnroll];
+                    bool any = false;
+#pragma unroll
+                    for (int q = 0; q < kSettleUnroll; q++) {
+                        const int j = base + q * BLOCK + tid;
+                        x[q] = j < P.hslots ? s_nxt_dyn[j] : 0.0;
+                        ok[q] = x[q] != 0.0;
+                        any |= ok[q];
+                    }
+                    if (!__any_sync(0xffffffffu, any)) continue;
+                    int v[kSettleUnroll], a[kSettleUnroll], b[kSettleUnroll];
+#pragma unroll
+                    for (int q = 0; q < kSettleUnroll; q++) {
+                        const int j = base + q * BLOCK + tid;
+                        v[q] = 0; a[q] = 0; b[q] = 0;
+                        if (ok[q]) {
+                            v[q] = s_keys[j]; s_nxt_dyn[j] = 0.0;
+                            if (will_push) { const int2 nr = __ldg(P.node_rec + v[q]); a[q] = nr.x; b[q] = nr.x + nr.y; }
+                        }
+                    }
+                    bool push[kSettleUnroll];
+                    int st[kSettleUnroll], dg[kSettleUnroll];
+                    double val[kSettleUnroll];
+#pragma unroll
+                    for (int q = 0; q < kSettleUnroll; q++) {
+                        cnt += ok[q] ? 1u : 0u;
+                        push[q] = false; st[q] = -1; dg[q] = 1; val[q] = x[q];
+                        if (ok[q] && will_push) {
+                            const unsigned d = (unsigned)(b[q] - a[q]);
+                            if (d == 0) push[q] = true;                                   // graph.h:91-93
+                            else if (x[q] >= P.rmax * (double)d) {                        // graph.h:94
+                                push[q] = true; st[q] = a[q]; dg[q] = (int)d; val[q] = x[q] / (double)d;  // graph.h:95
+                            }
+                        }
+                    }
+                    long long pl[kSettleUnroll], pp[kSettleUnroll];
+                    warp_append_multi<kSettleUnroll>(ok, P.capLog, &sm.n_log, err, pl);
+                    warp_append_multi<kSettleUnroll>(push, P.capF, &sm.n_push, err, pp);
+#pragma unroll
+                    for (int q = 0; q < kSettleUnroll; q++) {
+                        // reserve[v] += coef * r (graph.h:90): logged by slot, summed after the last level
+                        if (pl[q] >= 0) { log_id[pl[q]] = base + q * BLOCK + tid; log_val[pl[q]] = c * x[q]; }
+                        if (pp[q] >= 0) { push_start[pp[q]] = st[q]; push_deg[pp[q]] = dg[q]; push_val[pp[q]] = val[q]; }
+                    }
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                if (lane == 0 && cnt) atomicAdd(&sm.n_tfront, (int)cnt);
+            }
             for (int base = 0; base < n_nxt; base += BLOCK * kSettleUnroll) {
                 int v[kSettleUnroll];
                 bool ok[kSettleUnroll];
@@ -479,35 +555,25 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     ok[q] = j < n_nxt;
                     v[q] = ok[q] ? nxt_id[j] : 0;
                 }
-                double x[kSettleUnroll], r0[kSettleUnroll];
-                int pos[kSettleUnroll], hs[kSettleUnroll];
+                double x[kSettleUnroll];
+                int pos[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    pos[q] = 0; x[q] = 0.0; r0[q] = 0.0; hs[q] = -1;
-                    if (ok[q]) {
-                        if (SHASH && v[q] < 0) {   // table resident: residue and key in shared memory, reserve in rsv_g
-                            hs[q] = ~v[q];
-                            x[q] = s_nxt_dyn[hs[q]]; s_nxt_dyn[hs[q]] = 0.0;
-                            v[q] = s_keys[hs[q]];
-                            r0[q] = __ldcg(rsv_g + hs[q]);
-                        } else {
-                            x[q] = T.take(v[q], epoch, pos[q]);
-                        }
-                    }
+                    pos[q] = 0; x[q] = 0.0;
+                    if (ok[q]) x[q] = T.take(v[q], epoch, pos[q]);
                 }
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
                     a[q] = 0; b[q] = 0;
-                    if (ok[q] && will_push) { a[q] = __ldg(P.indptr + v[q]); b[q] = __ldg(P.indptr + v[q] + 1); }
+                    if (ok[q] && will_push) { const int2 nr = __ldg(P.node_rec + v[q]); a[q] = nr.x; b[q] = nr.x + nr.y; }
                 }
-                // reserve[v] += coef * r (graph.h:90): rsv_g for table residents, the compact support arrays otherwise
-                bool tbl[kSettleUnroll], first[kSettleUnroll], push[kSettleUnroll];
+                // reserve[v] += coef * r (graph.h:90), in the compact support arrays
+                bool first[kSettleUnroll], push[kSettleUnroll];
                 int st[kSettleUnroll], dg[kSettleUnroll];
                 double val[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    tbl[q] = SHASH && hs[q] >= 0;
-                    first[q] = ok[q] && !tbl[q] && pos[q] < 0;
+                    first[q] = ok[q] && pos[q] < 0;
                     push[q] = false; st[q] = -1; dg[q] = 1; val[q] = x[q];
                     if (ok[q] && will_push) {
                         const unsigned d = (unsigned)(b[q] - a[q]);
@@ -522,9 +588,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 warp_append_multi<kSettleUnroll>(push, P.capF, &sm.n_push, err, pp);
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    if (tbl[q]) {
-                        rsv_g[hs[q]] = r0[q] + c * x[q];
-                    } else if (first[q]) {
+                    if (first[q]) {
                         if (ps[q] >= 0) { sup_id[ps[q]] = v[q]; sup_val[ps[q]] = c * x[q]; }
                         T.put(v[q], epoch, (int)max(ps[q], 0ll), true);
                     } else if (ok[q]) {
@@ -537,6 +601,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             __syncthreads();
             if (tid == 0) {
                 sm.n_nxt = 0;
+                if (SHASH) st_frontier += (unsigned)sm.n_tfront;
                 if (lvl_E >= sm.wide_E) { sm.wide_E = lvl_E; sm.wide_expand = t_e; sm.wide_settle = clock64() - sm.t_prev; }
             }
             GP_PHASE(2);
@@ -544,22 +609,29 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         }
         if (tid == 0) { sm.ph[5] += sm.wide_expand; sm.ph[6] += sm.wide_settle; }
         for (int i = tid; i < kHistBins; i += BLOCK) sm.hist[i] = 0;
-        if (SHASH) {
-            // stage the reserve of the table residents in the (now all-zero) shared residue array: the radix passes
-            // below then read shared memory only; the global copy is wiped on the way
-            for (int j = tid; j < P.hslots; j += BLOCK) {
-                if (s_keys[j] != -1) { s_nxt_dyn[j] = __ldcg(rsv_g + j); rsv_g[j] = 0.0; }
+        const bool merged = SHASH && table_on;
+        if (merged) {
+            // the residue array is all zero after the last settle: sum the reserve log into it, by slot
+            __syncthreads();
+            const int n_log = min((long long)sm.n_log, P.capLog);
+            for (int j = tid; j < n_log; j += BLOCK) atomicAdd(s_nxt_dyn + log_id[j], log_val[j]);
+        }
+        if (SHASH && tid == 0) {
+            // adapt: a CTA whose sources spill most of their edges leaves the table off and tries again later
+            if (sm.table_on) {
+                if (sm.all_edges > 4096 && 2 * sm.spill_edges > sm.all_edges) { sm.table_on = 0; sm.trial = 0; }
+            } else if (++sm.trial >= 32) {
+                sm.table_on = 1;
             }
         }
         __syncthreads();
-
         // ------------------------------------------------------------------ top-k, graph.h:111-126
         const int n_sup = min((long long)sm.n_sup, P.capS);
         if (tid == 0) {
             const unsigned long long sup_all = (unsigned long long)n_sup + (SHASH ? (unsigned)sm.n_tab : 0u);
             st_support += sup_all; st_maxsup = max(st_maxsup, sup_all);
         }
-        const int n_tslots = SHASH ? P.hslots : 0;
+        const int n_tslots = merged ? P.hslots : 0;
         // pass 0: exponent histogram of the compact reserve values (coalesced; no table access)
         for (int j = tid; j < n_sup; j += BLOCK) {
             const double x = sup_val[j];
@@ -694,6 +766,12 @@ __global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots) 
     }
 }
 
+__global__ void node_rec_kernel(const int *indptr, long long n, int2 *rec) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        rec[i] = make_int2(indptr[i], indptr[i + 1] - indptr[i]);
+}
+
 // CSR sanity: indptr[0]==0, non-decreasing, indptr[n]==nnz, 0 <= indices < n.
 __global__ void validate_csr_kernel(const int *indptr, long long n, const int *indices, long long nnz, int *flag) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -715,6 +793,7 @@ struct gp_graph {
     long long n = 0, nnz = 0;
     int *d_indptr = nullptr;
     int *d_indices = nullptr;
+    int2 *d_node_rec = nullptr;
     bool owns_csr = false;
     int num_sms = GP_NUM_SMS_FALLBACK;
     size_t smem_optin = 0;
@@ -726,6 +805,7 @@ struct gp_graph {
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
     int scratch_hslots = 0;
+    long long scratch_capLog = 0;
     long long epoch_base = 0;              // sources pushed since the tables were last initialised
     double *d_coef = nullptr;              // [kMaxLevels]
     // [0] queue [1..4] stats [5] hash-tier queue [6] redo count [7] redo queue [8] max support | [16..21] cumulative
@@ -777,7 +857,8 @@ struct Plan {
     long long ctas, capF, capS;
     size_t dyn_smem;
     size_t bytes;
-    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand, off_rsvg;
+    size_t off_tab, off_push_start, off_push_deg, off_push_val, off_nxt_id, off_sup_id, off_cand, off_log_id, off_log_val;
+    long long capLog;
     int hslots;  // > 0: MODE 2 (shared-memory hash in front of the slabs)
 };
 
@@ -818,7 +899,13 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     long long ctas = (long long)g->num_sms * per_sm;  // scratch is sized for a full grid; small calls launch fewer
     // MODE 2: the largest power-of-two table {int key, double residue} that fits beside the static shared memory
     int hslots = 0;
-    if (mode == GP_SCRATCH_HBM && g_push_smem_hash != 0) {
+    // The table pays when a source's support is of the order of the table (measured on B200, profiles/r01_hash_tier.md);
+    // supports of the BASELINE shapes are 0.13 - 0.19 / rmax (Reddit 12.9 K @1e-5, MAG 18.7 K @1e-5, Amazon2M 152 K
+    // @1e-6), so "auto" (1) keeps the plain slabs when 0.15 / rmax is beyond twice the largest table; 2 forces it on.
+    bool want_table = mode == GP_SCRATCH_HBM && g_push_smem_hash != 0;
+    if (want_table && g_push_smem_hash == 1 && rmax > 0.0 && std::min(0.15 / rmax, (double)n) > 2.0 * 16384.0) want_table = false;
+    if (want_table && g_push_smem_hash == 1 && rmax <= 0.0 && n > 2 * 16384) want_table = false;
+    if (want_table) {
         const size_t avail = g->smem_optin / (size_t)per_sm;
         if (avail > stat + 2048) {
             hslots = 1;
@@ -826,16 +913,19 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
             if (hslots < 1024) hslots = 0;
         }
     }
+    // reserve log of MODE 2: at most one entry per table slot per level
+    const long long capLog = hslots ? (long long)std::max(L, 1) * hslots + 8192 : 0;
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
         p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 8), 256);
         p->off_push_start = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_push_deg = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_push_val = o; o += align_up((size_t)c * capF * 8, 256);
-        p->off_nxt_id = o; o += align_up((size_t)c * capF * 4, 256);
+        p->off_nxt_id = o; o += align_up((size_t)c * capS * 4, 256);
         p->off_sup_id = o; o += align_up((size_t)c * capS * 4, 256);
         p->off_cand = o; o += align_up((size_t)c * capS * 8, 256);
-        p->off_rsvg = o; o += align_up((size_t)c * hslots * 8, 256);
+        p->off_log_id = o; o += align_up((size_t)c * capLog * 4, 256);
+        p->off_log_val = o; o += align_up((size_t)c * capLog * 8, 256);
         return o;
     };
     size_t budget = (size_t)g->cfg.max_scratch_bytes;
@@ -847,7 +937,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     Plan tmp{};
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
     pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
-    pl->hslots = hslots;
+    pl->hslots = hslots; pl->capLog = capLog;
     pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : (size_t)hslots * 12;
     pl->bytes = bytes_for(ctas, pl);
     GP_REQUIRE(pl->bytes <= budget || ctas == 1, "scratch does not fit the budget");
@@ -857,7 +947,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
 int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream) {
     const bool same = g->scratch && g->scratch_bytes >= pl.bytes && g->scratch_ctas == pl.ctas &&
                       g->scratch_capF == pl.capF && g->scratch_capS == pl.capS && g->scratch_mode == pl.mode &&
-                      g->scratch_hslots == pl.hslots &&
+                      g->scratch_hslots == pl.hslots && g->scratch_capLog == pl.capLog &&
                       g->epoch_base + S < (1ll << 31) - 2;  // epoch tags are int32: re-initialise before they wrap
     if (same) return GP_OK;
     if (g->scratch && g->scratch_bytes < pl.bytes) {
@@ -875,9 +965,8 @@ int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream
         pl.mode == GP_SCRATCH_HBM ? (int4 *)(base + pl.off_tab) : nullptr,
         pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n);
     GP_CUDA_TRY(cudaGetLastError());
-    if (pl.hslots) GP_CUDA_TRY(cudaMemsetAsync(base + pl.off_rsvg, 0, (size_t)pl.ctas * pl.hslots * 8, stream));
     g->epoch_base = 0;
-    g->scratch_hslots = pl.hslots;
+    g->scratch_hslots = pl.hslots; g->scratch_capLog = pl.capLog;
     g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
     return GP_OK;
 }
@@ -1052,7 +1141,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 16, stream));
     char *base = (char *)g->scratch;
     PushParams P{};
-    P.indptr = g->d_indptr; P.indices = g->d_indices; P.n = (int)g->n;
+    P.indptr = g->d_indptr; P.node_rec = g->d_node_rec; P.indices = g->d_indices; P.n = (int)g->n;
     P.node_idx = d_node_idx; P.S = S; P.coef = g->d_coef; P.L = L; P.rmax = rmax; P.K = K;
     P.out_row = d_row; P.out_col = d_col; P.out_val = d_val; P.out_val32 = d_val32;
     P.tab = (Slot *)(base + pl.off_tab);
@@ -1067,7 +1156,8 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.capF = pl.capF; P.capS = pl.capS;
     P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 16;
     P.max_support = g->d_ctrl + 8; P.phase = g->d_ctrl + 24;
-    P.rsv_g = (double *)(base + pl.off_rsvg); P.hslots = pl.hslots; P.max_probe = std::max(g_push_smem_probe, 1);
+    P.log_id = (int *)(base + pl.off_log_id); P.log_val = (double *)(base + pl.off_log_val); P.capLog = pl.capLog;
+    P.hslots = pl.hslots; P.max_probe = std::max(g_push_smem_probe, 1); P.debug = g_push_debug;
     P.redo = nullptr; P.redo_count = nullptr;
     int launches = 0;
     long long done = 0;  // sources [0, done) are finished by the pilot
@@ -1181,6 +1271,10 @@ int graph_finish_create(gp_graph *g) {
     int flag = 0;
     GP_CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, g->stream));
     GP_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    GP_CUDA_TRY(cudaMalloc(&g->d_node_rec, sizeof(int2) * (size_t)g->n));
+    node_rec_kernel<<<g->num_sms * 4, 256, 0, g->stream>>>(g->d_indptr, g->n, g->d_node_rec);
+    GP_CUDA_TRY(cudaGetLastError());
+    GP_CUDA_TRY(cudaStreamSynchronize(g->stream));
     GP_REQUIRE(flag == 0, "malformed CSR: indptr must start at 0, be non-decreasing and end at nnz; indices must lie in [0, n)");
     return GP_OK;
 }
@@ -1241,7 +1335,7 @@ void gp_graph_destroy(gp_graph *g) {
     DeviceGuard guard(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->owns_csr) { cudaFree(g->d_indptr); cudaFree(g->d_indices); }
-    cudaFree(g->scratch); cudaFree(g->hscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
+    cudaFree(g->d_node_rec); cudaFree(g->scratch); cudaFree(g->hscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }

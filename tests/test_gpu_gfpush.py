@@ -202,8 +202,8 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
     DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
-                "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 0,
-                "push_smem_probe": 16, "push_max_ctas": 0}
+                "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 1,
+                "push_smem_probe": 4, "push_max_ctas": 0}
 
     def __init__(self, **kv):
         self.kv = kv
@@ -225,9 +225,9 @@ class _tuning:
 # so small that most sources are handed over to the slabs.
 TIERS = {
     "slab": dict(push_smem_hash=0),
-    "smem": dict(push_smem_hash=1),
-    "smem_probe1": dict(push_smem_hash=1, push_smem_probe=1),
-    "smem_probe2": dict(push_smem_hash=1, push_smem_probe=2),
+    "smem": dict(push_smem_hash=2),
+    "smem_probe1": dict(push_smem_hash=2, push_smem_probe=1),
+    "smem_probe2": dict(push_smem_hash=2, push_smem_probe=2),
     "l2hash_g1": dict(push_hash=1, push_cluster=1, push_pilot=16),
     "l2hash_g2": dict(push_hash=1, push_cluster=2, push_pilot=16),
     "l2hash_g4": dict(push_hash=1, push_cluster=4, push_pilot=16),
@@ -282,7 +282,7 @@ def test_gfpush_smem_hash_matches_reference_golden(name, mode, probe):
     indptr, indices = load_graph(name)
     z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
     K, rmax = int(z["K"]), float(z["rmax"])
-    with _tuning(push_smem_hash=1, push_smem_probe=probe):
+    with _tuning(push_smem_hash=2, push_smem_probe=probe):
         g = _graph(indptr, indices, scratch_mode=HBM)
         row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
     worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
