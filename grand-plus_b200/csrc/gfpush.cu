@@ -124,7 +124,6 @@ struct PushSmem {
     long long it;
     int n_push, n_nxt, n_sup, n_out, n_bucket;
     int n_log;     // MODE 2: entries in the reserve log
-    int n_tfront;  // MODE 2: table residents in the current frontier
     int n_tab;     // MODE 2: distinct nodes in the shared-memory table after the merge
     int table_on;  // MODE 2: this CTA currently uses the table (off when most edges spill: supports far beyond it)
     unsigned spill_edges, all_edges, trial;
@@ -300,8 +299,8 @@ struct Tables {
 //   every other node lives on the slab (both decisions are stable: entries are never removed while a source is live).
 //   expand: table residents cost a probe and a shared-memory atomic (measured 0.6 edges/clk/SM incl. probing at a
 //           table load of 0.8, profiles/r01_smem_hash_microbench.txt) instead of a DRAM round trip;
-//   settle: the table is walked (16 slots per thread, warps skip empty stretches); a resident's coef * residue is
-//           APPENDED to a reserve log as (slot, value) -- coalesced, no read-modify-write in global memory; the only
+//   settle: the frontier list holds ~slot for residents (first touch = the shared-memory add returned 0); a resident's
+//           coef * residue is APPENDED to a reserve log as (slot, value) -- coalesced, no read-modify-write in global memory; the only
 //           scattered access left per node is its indptr pair;
 //   after the last level the log is summed into the (then all-zero) residue array by slot, the top-k reads shared
 //   memory, and the slab residents' reserve is in the support arrays exactly as in MODE 0.
@@ -456,8 +455,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         for (int q = 0; q < kEdgeUnroll; q++) {
                             fresh[q] = false;
                             if (ok[q]) {
-                                if (h[q] >= 0) { if (P.debug & 1) s_nxt_dyn[h[q]] += add[q]; else atomicAdd(s_nxt_dyn + h[q], add[q]); }      // table: settle walks the slots
-                                else { fresh[q] = T.add_next(v[q], add[q]); n_spill++; }  // slab: first touch -> list
+                                if (h[q] >= 0) { fresh[q] = atomicAdd(s_nxt_dyn + h[q], add[q]) == 0.0; v[q] = ~h[q]; }  // table resident: list entry ~slot
+                                else { fresh[q] = T.add_next(v[q], add[q]); n_spill++; }                                  // slab resident: list entry v
                             }
                         }
                     } else {
@@ -490,61 +489,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const int next_level = level + 1;
             const bool will_push = next_level < P.L - 1;
             const double c = P.coef[next_level];
-            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; sm.n_tfront = 0; }
+            if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
             __syncthreads();
-            if (SHASH && table_on) {
-                // table residents: walk the residues; a warp whose stretch holds none moves on at once
-                unsigned cnt = 0;
-                for (int base = 0; base < P.hslots; base += BLOCK * kSettleUnroll) {
-                    double x[kSettleUnroll];
-                    bool ok[kSettleUnroll];
-                    bool any = false;
-#pragma unroll
-                    for (int q = 0; q < kSettleUnroll; q++) {
-                        const int j = base + q * BLOCK + tid;
-                        x[q] = j < P.hslots ? s_nxt_dyn[j] : 0.0;
-                        ok[q] = x[q] != 0.0;
-                        any |= ok[q];
-                    }
-                    if (!__any_sync(0xffffffffu, any)) continue;
-                    int v[kSettleUnroll], a[kSettleUnroll], b[kSettleUnroll];
-#pragma unroll
-                    for (int q = 0; q < kSettleUnroll; q++) {
-                        const int j = base + q * BLOCK + tid;
-                        v[q] = 0; a[q] = 0; b[q] = 0;
-                        if (ok[q]) {
-                            v[q] = s_keys[j]; s_nxt_dyn[j] = 0.0;
-                            if (will_push) { const int2 nr = __ldg(P.node_rec + v[q]); a[q] = nr.x; b[q] = nr.x + nr.y; }
-                        }
-                    }
-                    bool push[kSettleUnroll];
-                    int st[kSettleUnroll], dg[kSettleUnroll];
-                    double val[kSettleUnroll];
-#pragma unroll
-                    for (int q = 0; q < kSettleUnroll; q++) {
-                        cnt += ok[q] ? 1u : 0u;
-                        push[q] = false; st[q] = -1; dg[q] = 1; val[q] = x[q];
-                        if (ok[q] && will_push) {
-                            const unsigned d = (unsigned)(b[q] - a[q]);
-                            if (d == 0) push[q] = true;                                   // graph.h:91-93
-                            else if (x[q] >= P.rmax * (double)d) {                        // graph.h:94
-                                push[q] = true; st[q] = a[q]; dg[q] = (int)d; val[q] = x[q] / (double)d;  // graph.h:95
-                            }
-                        }
-                    }
-                    long long pl[kSettleUnroll], pp[kSettleUnroll];
-                    warp_append_multi<kSettleUnroll>(ok, P.capLog, &sm.n_log, err, pl);
-                    warp_append_multi<kSettleUnroll>(push, P.capF, &sm.n_push, err, pp);
-#pragma unroll
-                    for (int q = 0; q < kSettleUnroll; q++) {
-                        // reserve[v] += coef * r (graph.h:90): logged by slot, summed after the last level
-                        if (pl[q] >= 0) { log_id[pl[q]] = base + q * BLOCK + tid; log_val[pl[q]] = c * x[q]; }
-                        if (pp[q] >= 0) { push_start[pp[q]] = st[q]; push_deg[pp[q]] = dg[q]; push_val[pp[q]] = val[q]; }
-                    }
-                }
-                cnt = __reduce_add_sync(0xffffffffu, cnt);
-                if (lane == 0 && cnt) atomicAdd(&sm.n_tfront, (int)cnt);
-            }
             for (int base = 0; base < n_nxt; base += BLOCK * kSettleUnroll) {
                 int v[kSettleUnroll];
                 bool ok[kSettleUnroll];
@@ -556,24 +502,34 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     v[q] = ok[q] ? nxt_id[j] : 0;
                 }
                 double x[kSettleUnroll];
-                int pos[kSettleUnroll];
+                int pos[kSettleUnroll], hs[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    pos[q] = 0; x[q] = 0.0;
-                    if (ok[q]) x[q] = T.take(v[q], epoch, pos[q]);
+                    pos[q] = 0; x[q] = 0.0; hs[q] = -1;
+                    if (ok[q]) {
+                        if (SHASH && v[q] < 0) {   // table resident: residue and key in shared memory
+                            hs[q] = ~v[q];
+                            x[q] = s_nxt_dyn[hs[q]]; s_nxt_dyn[hs[q]] = 0.0;
+                            v[q] = s_keys[hs[q]];
+                        } else {
+                            x[q] = T.take(v[q], epoch, pos[q]);
+                        }
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
                     a[q] = 0; b[q] = 0;
                     if (ok[q] && will_push) { const int2 nr = __ldg(P.node_rec + v[q]); a[q] = nr.x; b[q] = nr.x + nr.y; }
                 }
-                // reserve[v] += coef * r (graph.h:90), in the compact support arrays
-                bool first[kSettleUnroll], push[kSettleUnroll];
+                // reserve[v] += coef * r (graph.h:90): logged by slot for table residents (summed after the last level),
+                // in the compact support arrays for slab residents
+                bool tbl[kSettleUnroll], first[kSettleUnroll], push[kSettleUnroll];
                 int st[kSettleUnroll], dg[kSettleUnroll];
                 double val[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    first[q] = ok[q] && pos[q] < 0;
+                    tbl[q] = SHASH && hs[q] >= 0;
+                    first[q] = ok[q] && !tbl[q] && pos[q] < 0;
                     push[q] = false; st[q] = -1; dg[q] = 1; val[q] = x[q];
                     if (ok[q] && will_push) {
                         const unsigned d = (unsigned)(b[q] - a[q]);
@@ -583,12 +539,15 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         }
                     }
                 }
-                long long ps[kSettleUnroll], pp[kSettleUnroll];
+                long long ps[kSettleUnroll], pp[kSettleUnroll], pl[kSettleUnroll];
+                if (SHASH) warp_append_multi<kSettleUnroll>(tbl, P.capLog, &sm.n_log, err, pl);
                 warp_append_multi<kSettleUnroll>(first, P.capS, &sm.n_sup, err, ps);
                 warp_append_multi<kSettleUnroll>(push, P.capF, &sm.n_push, err, pp);
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    if (first[q]) {
+                    if (tbl[q]) {
+                        if (pl[q] >= 0) { log_id[pl[q]] = hs[q]; log_val[pl[q]] = c * x[q]; }
+                    } else if (first[q]) {
                         if (ps[q] >= 0) { sup_id[ps[q]] = v[q]; sup_val[ps[q]] = c * x[q]; }
                         T.put(v[q], epoch, (int)max(ps[q], 0ll), true);
                     } else if (ok[q]) {
@@ -601,7 +560,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             __syncthreads();
             if (tid == 0) {
                 sm.n_nxt = 0;
-                if (SHASH) st_frontier += (unsigned)sm.n_tfront;
                 if (lvl_E >= sm.wide_E) { sm.wide_E = lvl_E; sm.wide_expand = t_e; sm.wide_settle = clock64() - sm.t_prev; }
             }
             GP_PHASE(2);
