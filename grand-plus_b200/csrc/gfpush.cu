@@ -258,42 +258,34 @@ __device__ __forceinline__ void st_int4_hint(void *p, int4 v, unsigned long long
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
-// Per-CTA view of the next-residue table.
-template <bool SMEM_NXT>
+// Per-CTA view of the direct-addressed slab (MODE 0, and the slab residents of MODE 2).
+template <bool UNUSED>
 struct Tables {
-    Slot *tab;      // HBM mode
-    int2 *meta;     // SMEM mode
-    double *s_nxt;  // SMEM mode
+    Slot *tab;
+    int2 *meta;     // unused (kept so that the parameter block layout is stable)
+    double *s_nxt;  // unused
     unsigned long long pol;  // L2 evict_last policy for the slab sectors
     // next[v] += x; true when v had no residue yet (first touch at this level)
     __device__ __forceinline__ bool add_next(int v, double x) const {
-        if (SMEM_NXT) return atomicAdd(s_nxt + v, x) == 0.0;
         return atom_add_f64_hint(&tab[v].nxt, x, pol) == 0.0;  // graph.h:98
     }
-    // Takes next[v] (leaving 0).  pos >= 0: v already has a reserve entry at that position.
+    // Takes next[v] (the caller clears it with put).  pos >= 0: v already has a reserve entry at that position.
     __device__ __forceinline__ double take(int v, int epoch, int &pos) const {
-        if (SMEM_NXT) {
-            const double x = s_nxt[v];
-            s_nxt[v] = 0.0;
-            const int2 m = meta[v];
-            pos = (m.x == epoch) ? m.y : -1;
-            return x;
-        } else {
-            const double4 *unused = nullptr; (void)unused;
-            // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
-            const int4 raw = ldcg_int4_hint(tab + v, pol);
-            pos = (raw.z == epoch) ? raw.w : -1;
-            return __hiloint2double(raw.y, raw.x);
-        }
+        // one 16-byte L2 read: the residue half was produced by atomics, so bypass L1
+        const int4 raw = ldcg_int4_hint(tab + v, pol);
+        pos = (raw.z == epoch) ? raw.w : -1;
+        return __hiloint2double(raw.y, raw.x);
     }
-    // Clears next[v] and records (epoch, pos): one 16-byte write (HBM) / 8-byte write (SMEM).
+    // Clears next[v] and records (epoch, pos): one 16-byte write.
     __device__ __forceinline__ void put(int v, int epoch, int pos, bool changed) const {
-        if (SMEM_NXT) { if (changed) meta[v] = make_int2(epoch, pos); }
-        else st_int4_hint(tab + v, make_int4(0, 0, epoch, pos), pol);
+        (void)changed;
+        st_int4_hint(tab + v, make_int4(0, 0, epoch, pos), pol);
     }
 };
 
-// MODE 0: direct-addressed slabs in HBM.  MODE 1: dense next-residue array in shared memory (small graphs).
+// MODE 0: direct-addressed slabs in HBM.
+// MODE 1: dense next-residue array double[n] in shared memory (small graphs): MODE 2's machinery with slot == node id
+//   (no keys, no probes, no slab residents, a bitmap of reached nodes for the support count).
 // MODE 2: an open-addressed {key, next residue} table in SHARED MEMORY in front of the slabs.  A node that finds a
 //   slot within max_probe probes when the source first touches it lives in the table until the source is done,
 //   every other node lives on the slab (both decisions are stable: entries are never removed while a source is live).
@@ -308,11 +300,12 @@ struct Tables {
 //   re-tries 32 sources later.
 template <int BLOCK, int MODE>
 __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams P) {
-    constexpr bool SMEM_NXT = MODE == 1;
-    constexpr bool SHASH = MODE == 2;
+    constexpr bool DENSE = MODE == 1;          // MODE 1 = the same machinery as MODE 2 with slot == node id: no keys, no probes,
+    constexpr bool SHASH = MODE != 0;          //          no slab residents; a bitmap tells which nodes the source has reached
     __shared__ PushSmem<BLOCK> sm;
     extern __shared__ double s_nxt_dyn[];
-    int *s_keys = reinterpret_cast<int *>(s_nxt_dyn + (SHASH ? P.hslots : 0));  // SHASH: [hslots] after the residues
+    int *s_keys = reinterpret_cast<int *>(s_nxt_dyn + (SHASH ? P.hslots : 0));  // MODE 2: key[hslots]; MODE 1: bitmap[(n+31)/32]
+    unsigned *s_seen = reinterpret_cast<unsigned *>(s_keys);
     const unsigned hmask = (unsigned)(P.hslots - 1);
     int *log_id = SHASH ? P.log_id + (long long)blockIdx.x * P.capLog : nullptr;
     double *log_val = SHASH ? P.log_val + (long long)blockIdx.x * P.capLog : nullptr;
@@ -320,30 +313,29 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     const int tid = threadIdx.x;
     const int lane = gp_lane();
     const long long cta = blockIdx.x;
-    Tables<SMEM_NXT> T;
-    T.tab = SMEM_NXT ? nullptr : P.tab + cta * (long long)P.n;
-    T.meta = SMEM_NXT ? P.meta + cta * (long long)P.n : nullptr;
+    Tables<false> T;
+    T.tab = DENSE ? nullptr : P.tab + cta * (long long)P.n;
+    T.meta = nullptr;
     T.s_nxt = s_nxt_dyn;
     T.pol = l2_policy_evict_last();
     int *push_start = P.push_start + cta * P.capF;
     int *push_deg = P.push_deg + cta * P.capF;
     double *push_val = P.push_val + cta * P.capF;
-    int *nxt_id = P.nxt_id + cta * P.capF;
+    int *nxt_id = P.nxt_id + cta * P.capS;   // (allocated with capS entries per CTA)
     int *sup_id = P.sup_id + cta * P.capS;
     double *sup_val = P.sup_val + cta * P.capS;
     unsigned long long *err = P.stats + 3;
 
-    if (SMEM_NXT) {
-        for (int i = tid; i < P.n; i += BLOCK) s_nxt_dyn[i] = 0.0;
-    }
     if (SHASH) {
-        for (int i = tid; i < P.hslots; i += BLOCK) { s_nxt_dyn[i] = 0.0; s_keys[i] = -1; }
+        for (int i = tid; i < P.hslots; i += BLOCK) { s_nxt_dyn[i] = 0.0; if (!DENSE) s_keys[i] = -1; }
+        if (DENSE) for (int i = tid; i < (P.hslots + 31) / 32; i += BLOCK) s_seen[i] = 0u;
         if (tid == 0) { sm.table_on = 1; sm.trial = 0; }
     }
     bool table_on = false;   // this level / merge uses the table
     // SHASH: slot of node v in the shared-memory table (claiming one if v is new), or -1 = no slot within max_probe
     auto s_find = [&](int v, bool &claimed) -> int {
         claimed = false;
+        if (DENSE) return v;
         if (!table_on) return -1;
         unsigned h = ((unsigned)v * 2654435761u) >> 7 & hmask;
         for (int probe = 0; probe < P.max_probe; probe++, h = (h + 1) & hmask) {
@@ -388,6 +380,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             if (SHASH && sm.table_on) {   // the table is empty: the source claims its home slot; reserve[src] = coef[0]
                 bool claimed;
                 const int h = s_find(src, claimed);
+                if (DENSE) s_seen[src >> 5] |= 1u << (src & 31);
                 log_id[0] = h; log_val[0] = P.coef[0]; sm.n_log = 1; sm.n_tab = 1;
             } else {
                 T.put(src, epoch, 0, true);
@@ -491,6 +484,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const double c = P.coef[next_level];
             if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
             __syncthreads();
+            int n_new = 0;   // MODE 1: nodes reached for the first time
             for (int base = 0; base < n_nxt; base += BLOCK * kSettleUnroll) {
                 int v[kSettleUnroll];
                 bool ok[kSettleUnroll];
@@ -510,7 +504,13 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         if (SHASH && v[q] < 0) {   // table resident: residue and key in shared memory
                             hs[q] = ~v[q];
                             x[q] = s_nxt_dyn[hs[q]]; s_nxt_dyn[hs[q]] = 0.0;
-                            v[q] = s_keys[hs[q]];
+                            if (DENSE) {   // slot == node; first time this source reaches it?
+                                v[q] = hs[q];
+                                const unsigned bit = 1u << (v[q] & 31);
+                                if (!(atomicOr(&s_seen[v[q] >> 5], bit) & bit)) n_new++;
+                            } else {
+                                v[q] = s_keys[hs[q]];
+                            }
                         } else {
                             x[q] = T.take(v[q], epoch, pos[q]);
                         }
@@ -557,6 +557,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     if (pp[q] >= 0) { push_start[pp[q]] = st[q]; push_deg[pp[q]] = dg[q]; push_val[pp[q]] = val[q]; }
                 }
             }
+            if (DENSE) {
+                n_new = (int)__reduce_add_sync(0xffffffffu, (unsigned)n_new);
+                if (lane == 0 && n_new) atomicAdd(&sm.n_tab, n_new);
+            }
             __syncthreads();
             if (tid == 0) {
                 sm.n_nxt = 0;
@@ -574,7 +578,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const int n_log = min((long long)sm.n_log, P.capLog);
             for (int j = tid; j < n_log; j += BLOCK) atomicAdd(s_nxt_dyn + log_id[j], log_val[j]);
         }
-        if (SHASH && tid == 0) {
+        if (SHASH && !DENSE && tid == 0) {
             // adapt: a CTA whose sources spill most of their edges leaves the table off and tries again later
             if (sm.table_on) {
                 if (sm.all_edges > 4096 && 2 * sm.spill_edges > sm.all_edges) { sm.table_on = 0; sm.trial = 0; }
@@ -655,10 +659,11 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             }
         }
         for (int j = tid; j < n_tslots; j += BLOCK) {
-            const int id = s_keys[j];
+            const int id = DENSE ? j : s_keys[j];
             if (id == -1) continue;
             const double x = s_nxt_dyn[j];
-            s_keys[j] = -1; s_nxt_dyn[j] = 0.0;   // the table is empty again for the next source
+            if (!DENSE) s_keys[j] = -1;
+            s_nxt_dyn[j] = 0.0;   // the table is empty again for the next source
             if (x > 0.0) {
                 const unsigned long long key = (unsigned long long)__double_as_longlong(x);
                 const unsigned long long t = key >> shift;
@@ -670,6 +675,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 }
             }
         }
+        if (DENSE && merged) for (int i = tid; i < (P.hslots + 31) / 32; i += BLOCK) s_seen[i] = 0u;
         __syncthreads();
         {
             // rank-count the boundary bucket: keep its `want_bucket` largest (ties: lower slot first)
@@ -828,7 +834,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     int block = g->cfg.block_threads ? g->cfg.block_threads : (n <= 4096 ? 256 : 1024);
     GP_REQUIRE(block == 256 || block == 512 || block == 1024, "block_threads must be 256, 512 or 1024 (got %d)", block);
     const size_t stat = block == 256 ? static_smem_bytes<256>() : block == 512 ? static_smem_bytes<512>() : static_smem_bytes<1024>();
-    const size_t smem_need = stat + (size_t)n * sizeof(double) + 1024;
+    const size_t smem_need = stat + (size_t)n * sizeof(double) + ((size_t)n + 31) / 32 * 4 + 1024;
     int mode = g->cfg.scratch_mode;
     if (mode == GP_SCRATCH_AUTO) mode = (smem_need <= g->smem_optin) ? GP_SCRATCH_SMEM : GP_SCRATCH_HBM;
     GP_REQUIRE(mode == GP_SCRATCH_SMEM || mode == GP_SCRATCH_HBM, "unknown scratch_mode %d", mode);
@@ -860,6 +866,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     // The table pays when a source's support is of the order of the table (measured on B200, profiles/r01_hash_tier.md);
     // supports of the BASELINE shapes are 0.13 - 0.19 / rmax (Reddit 12.9 K @1e-5, MAG 18.7 K @1e-5, Amazon2M 152 K
     // @1e-6), so "auto" (1) keeps the plain slabs when 0.15 / rmax is beyond twice the largest table; 2 forces it on.
+    if (mode == GP_SCRATCH_SMEM) hslots = (int)n;   // MODE 1: slot == node id
     bool want_table = mode == GP_SCRATCH_HBM && g_push_smem_hash != 0;
     if (want_table && g_push_smem_hash == 1 && rmax > 0.0 && std::min(0.15 / rmax, (double)n) > 2.0 * 16384.0) want_table = false;
     if (want_table && g_push_smem_hash == 1 && rmax <= 0.0 && n > 2 * 16384) want_table = false;
@@ -875,7 +882,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     const long long capLog = hslots ? (long long)std::max(L, 1) * hslots + 8192 : 0;
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
-        p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 8), 256);
+        p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 0), 256);
         p->off_push_start = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_push_deg = o; o += align_up((size_t)c * capF * 4, 256);
         p->off_push_val = o; o += align_up((size_t)c * capF * 8, 256);
@@ -896,7 +903,7 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
     pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
     pl->hslots = hslots; pl->capLog = capLog;
-    pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) : (size_t)hslots * 12;
+    pl->dyn_smem = mode == GP_SCRATCH_SMEM ? (size_t)n * sizeof(double) + ((size_t)n + 31) / 32 * 4 : (size_t)hslots * 12;
     pl->bytes = bytes_for(ctas, pl);
     GP_REQUIRE(pl->bytes <= budget || ctas == 1, "scratch does not fit the budget");
     return GP_OK;
@@ -919,10 +926,10 @@ int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream
     }
     // table invariants between sources: next residue == 0 everywhere, reserve == kUnseen everywhere
     char *base = (char *)g->scratch;
-    init_tables_kernel<<<g->num_sms * 8, 256, 0, stream>>>(
-        pl.mode == GP_SCRATCH_HBM ? (int4 *)(base + pl.off_tab) : nullptr,
-        pl.mode == GP_SCRATCH_HBM ? nullptr : (int2 *)(base + pl.off_tab), pl.ctas * g->n);
-    GP_CUDA_TRY(cudaGetLastError());
+    if (pl.mode == GP_SCRATCH_HBM) {   // MODE 1 keeps no per-node state in HBM
+        init_tables_kernel<<<g->num_sms * 8, 256, 0, stream>>>((int4 *)(base + pl.off_tab), nullptr, pl.ctas * g->n);
+        GP_CUDA_TRY(cudaGetLastError());
+    }
     g->epoch_base = 0;
     g->scratch_hslots = pl.hslots; g->scratch_capLog = pl.capLog;
     g->scratch_ctas = pl.ctas; g->scratch_capF = pl.capF; g->scratch_capS = pl.capS; g->scratch_mode = pl.mode;
