@@ -114,7 +114,7 @@ enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
 
 template <int BLOCK>
 struct PushSmem {
-    unsigned off[BLOCK];
+    unsigned off[BLOCK + 1];   // exclusive scan of the tile's degrees, off[BLOCK] = total (sentinel of the owner walk)
     int start[BLOCK];
     double val[BLOCK];
     unsigned warp_scan[BLOCK / 32 + 1];
@@ -155,13 +155,16 @@ __device__ __forceinline__ long long warp_append_pos(bool is_new, long long cap,
 template <int U>
 __device__ __forceinline__ void warp_append_multi(const bool (&is_new)[U], long long cap, int *s_count,
                                                   unsigned long long *err, long long (&pos)[U]) {
+#pragma unroll
+    for (int q = 0; q < U; q++) pos[q] = -1;
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < U; q++) any |= is_new[q];
+    if (!__any_sync(0xffffffffu, any)) return;   // nothing to append in this warp: one vote instead of U ballots
     unsigned m[U];
     int total = 0;
 #pragma unroll
     for (int q = 0; q < U; q++) { m[q] = __ballot_sync(0xffffffffu, is_new[q]); total += __popc(m[q]); }
-#pragma unroll
-    for (int q = 0; q < U; q++) pos[q] = -1;
-    if (total == 0) return;
     const int lane = gp_lane();
     int base = 0;
     if (lane == 0) base = atomicAdd(s_count, total);
@@ -414,10 +417,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 unsigned total;
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
+                if (tid == 0) sm.off[BLOCK] = total;
                 __syncthreads();
                 if (tid == 0) { st_edges += total; lvl_E += total; }
                 // edge e of the tile goes to thread e % BLOCK: every warp gets work as soon as the tile has
-                // BLOCK edges, and a warp's 32 lanes read 32 consecutive `indices` entries
+                // BLOCK edges, and a warp's 32 lanes read 32 consecutive `indices` entries.  (A contiguous share per warp
+                // with a walking owner search was measured slower: the walk chains the unrolled edges together.)
                 for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += BLOCK * kEdgeUnroll) {
                     int v[kEdgeUnroll];
                     double add[kEdgeUnroll];
