@@ -582,6 +582,8 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             __syncthreads();
             const int n_log = min((long long)sm.n_log, P.capLog);
             for (int j = tid; j < n_log; j += BLOCK) atomicAdd(s_nxt_dyn + log_id[j], log_val[j]);
+            __syncthreads();
+            GP_PHASE(3);   // reserve merge
         }
         if (SHASH && !DENSE && tid == 0) {
             // adapt: a CTA whose sources spill most of their edges leaves the table off and tries again later

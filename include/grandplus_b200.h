@@ -116,7 +116,7 @@ int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset);
 /* Profiling hook (the reference only takes an unused gettimeofday pair, graph.h:54-56,129-130): SM cycles the
  * persistent CTAs spent per phase, summed over CTAs since the last reset:
  * [0] fetch + level 0, [1] expand (gfpush_kernel) / table growth (hash tier), [2] settle / expand,
- * [3] - / settle, [4] top-k, [5] expand of each source's widest level, [6] its settle, [7] kernel residency.
+ * [3] reserve merge / settle, [4] top-k, [5] expand of each source's widest level, [6] its settle, [7] kernel residency.
  * Device-wide synchronise. */
 int gp_gfpush_phase_cycles(gp_graph *g, uint64_t out[8], int reset);
 

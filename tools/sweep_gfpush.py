@@ -69,7 +69,7 @@ def main():
               f"scratch={st['scratch_bytes'] / 1e6:.0f}MB", flush=True)
         ph = graph.phase_cycles(reset=True)
         if ph["resident"]:
-            names = ph.keys() if st["hash_sources"] else ("fetch", "expand", "settle", "-", "topk", "wide_expand", "wide_settle")
+            names = ph.keys() if st["hash_sources"] else ("fetch", "expand", "settle", "merge", "topk", "wide_expand", "wide_settle")
             us = ph["resident"] / 1965.0 / max(st["sources"], 1)
             print(f"    {us:.0f} us of CTA time per source; % by phase: " +
                   " ".join(f"{n}={100.0 * v / ph['resident']:.1f}" for n, v in zip(names, ph.values()) if n != "-"), flush=True)
