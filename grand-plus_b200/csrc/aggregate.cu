@@ -20,7 +20,7 @@
 #include <algorithm>
 #include <string>
 
-extern int g_push_hash, g_push_cluster, g_push_hash_slots, g_push_l2_mb, g_push_load_pct, g_push_list_div, g_push_pilot, g_push_hash_block, g_push_max_clusters, g_push_smem_hash, g_push_smem_probe, g_push_debug, g_push_max_ctas,
+extern int g_push_hash, g_push_cluster, g_push_hash_slots, g_push_l2_mb, g_push_load_pct, g_push_list_div, g_push_pilot, g_push_hash_block, g_push_max_clusters, g_push_smem_hash, g_push_smem_probe, g_push_max_ctas,
     g_push_tuning_gen;  // gfpush.cu
 
 namespace {
@@ -753,7 +753,6 @@ int gp_set_tuning(const char *key, int64_t value) {
     else if (k == "push_smem_hash") { g_push_smem_hash = (int)value; g_push_tuning_gen++; }
     else if (k == "push_smem_probe") { GP_REQUIRE(value >= 1 && value <= 1024, "push_smem_probe must be in [1, 1024]"); g_push_smem_probe = (int)value; }
     else if (k == "push_max_ctas") { GP_REQUIRE(value >= 0, "push_max_ctas must be >= 0"); g_push_max_ctas = (int)value; }
-    else if (k == "push_debug") { g_push_debug = (int)value; }
     else if (k == "push_pilot") { GP_REQUIRE(value >= 1, "push_pilot must be >= 1"); g_push_pilot = (int)value; g_push_tuning_gen++; }
     else { gp_set_error("unknown tuning key '%s'", key); return GP_ERR_INVALID; }
     return GP_OK;

@@ -34,7 +34,6 @@
 // tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
 int g_push_smem_hash = 1;     // "push_smem_hash": shared-memory residue table in front of the slabs (HBM mode, MODE 2 kernel):
                               // 0 off, 1 auto (on when the expected support is of the order of the table), 2 always on
-int g_push_debug = 0;
 int g_push_smem_probe = 4;    // "push_smem_probe": probes before a node is sent to the slab
 int g_push_hash = 0;          // "push_hash": 1 = route HBM-mode sources through the L2-resident hash tier first
                               // (opt-in: measured slower than the slabs on every BASELINE shape, profiles/r01_hash_tier.md)
@@ -84,7 +83,6 @@ struct PushParams {
     float *out_val32;  // nullable
     // per-CTA scratch
     Slot *tab;         // HBM mode: [ctas][n] 16-byte slots {next residue, epoch, support position}
-    int2 *meta;        // SMEM mode: [ctas][n] {epoch, support position} (next residue lives in shared memory)
     int epoch_base;    // slot.epoch == epoch_base + it + 1  <=>  node already in source `it`'s reserve
     int *push_start;   // [ctas][capF]  frontier nodes that passed the threshold: CSR offset (-1 = dangling -> source)
     int *push_deg;     // [ctas][capF]
@@ -107,7 +105,6 @@ struct PushParams {
     long long capLog;
     int hslots;        // table slots, power of two
     int max_probe;     // a node that finds no slot within this many probes goes to the slab for this level
-    int debug;         // experiments only
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -265,8 +262,6 @@ __device__ __forceinline__ void st_int4_hint(void *p, int4 v, unsigned long long
 template <bool UNUSED>
 struct Tables {
     Slot *tab;
-    int2 *meta;     // unused (kept so that the parameter block layout is stable)
-    double *s_nxt;  // unused
     unsigned long long pol;  // L2 evict_last policy for the slab sectors
     // next[v] += x; true when v had no residue yet (first touch at this level)
     __device__ __forceinline__ bool add_next(int v, double x) const {
@@ -318,8 +313,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     const long long cta = blockIdx.x;
     Tables<false> T;
     T.tab = DENSE ? nullptr : P.tab + cta * (long long)P.n;
-    T.meta = nullptr;
-    T.s_nxt = s_nxt_dyn;
     T.pol = l2_policy_evict_last();
     int *push_start = P.push_start + cta * P.capF;
     int *push_deg = P.push_deg + cta * P.capF;
@@ -1117,7 +1110,6 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.node_idx = d_node_idx; P.S = S; P.coef = g->d_coef; P.L = L; P.rmax = rmax; P.K = K;
     P.out_row = d_row; P.out_col = d_col; P.out_val = d_val; P.out_val32 = d_val32;
     P.tab = (Slot *)(base + pl.off_tab);
-    P.meta = (int2 *)(base + pl.off_tab);
     P.epoch_base = (int)g->epoch_base;
     P.push_start = (int *)(base + pl.off_push_start);
     P.push_deg = (int *)(base + pl.off_push_deg);
@@ -1129,7 +1121,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 16;
     P.max_support = g->d_ctrl + 8; P.phase = g->d_ctrl + 24;
     P.log_id = (int *)(base + pl.off_log_id); P.log_val = (double *)(base + pl.off_log_val); P.capLog = pl.capLog;
-    P.hslots = pl.hslots; P.max_probe = std::max(g_push_smem_probe, 1); P.debug = g_push_debug;
+    P.hslots = pl.hslots; P.max_probe = std::max(g_push_smem_probe, 1);
     P.redo = nullptr; P.redo_count = nullptr;
     int launches = 0;
     long long done = 0;  // sources [0, done) are finished by the pilot

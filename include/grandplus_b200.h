@@ -195,11 +195,15 @@ int gp_narrow_index(const int64_t *d_idx, int64_t n, int64_t n_rows, int32_t *d_
 int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, uint64_t offset,
                      uint8_t *d_mask, void *stream);
 
-/* Performance knobs for sweeps (profiles/); defaults are the measured best.  Keys: "agg_kernel"
- * (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf", "agg_max_vec",
- * "agg_max_chunk", "agg_smem_kb"; GFPush's L2-resident hash tier: "push_hash" (0 = slabs only), "push_cluster"
- * (CTAs per source: 0 auto, 1, 2, 4, 8, 16), "push_hash_slots" (table capacity per cluster, 0 auto), "push_l2_mb",
- * "push_load_pct", "push_list_div", "push_pilot".  Results never depend on them. */
+/* Performance knobs for sweeps (profiles/); defaults are the measured best and results never depend on them.
+ * Aggregation: "agg_kernel" (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf",
+ * "agg_max_vec", "agg_max_chunk", "agg_smem_kb".
+ * GFPush (HBM mode): "push_smem_hash" (shared-memory residue table in front of the slabs: 0 off, 1 auto from rmax,
+ * 2 always), "push_smem_probe" (probes before a node goes to the slab), "push_max_ctas" (cap on persistent CTAs, for
+ * scaling experiments); the opt-in L2-resident cluster tier: "push_hash" (1 = on), "push_cluster" (CTAs per source:
+ * 0 auto, 1, 2, 4, 8, 16), "push_hash_slots", "push_hash_block", "push_l2_mb", "push_load_pct", "push_list_div",
+ * "push_pilot", "push_max_clusters".  The same keys are read from the GP_TUNING environment variable
+ * ("key=value,key=value") by the Python loader. */
 int gp_set_tuning(const char *key, int64_t value);
 
 #ifdef __cplusplus
