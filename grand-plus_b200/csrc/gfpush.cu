@@ -56,6 +56,7 @@ constexpr int kMaxK = kBucketCap;   // K above this is refused
 constexpr int kMaxLevels = 256;
 constexpr int kEdgeUnroll = 4;
 constexpr int kSettleUnroll = 4;
+constexpr int kSmallList = kHistBins;   // frontier-list entries kept in shared memory (the rest go to HBM)
 
 // One direct-addressed table slot.  The reserve itself is NOT in the table: a slot only remembers
 // where the node sits in the compact (sup_id, sup_val) arrays, and an epoch tag (= source number)
@@ -115,7 +116,10 @@ struct PushSmem {
     int start[BLOCK];
     double val[BLOCK];
     unsigned warp_scan[BLOCK / 32 + 1];
-    unsigned hist[kHistBins];
+    union {
+        unsigned hist[kHistBins];   // top-k: radix histogram
+        int fl[kHistBins];          // levels: the first kSmallList entries of the frontier list (dead before the top-k)
+    };
     unsigned long long bkey[kBucketCap];
     int bid[kBucketCap];
     long long it;
@@ -385,8 +389,9 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             if (P.L > 1) {
                 const int a = P.indptr[src], b = P.indptr[src + 1];
                 const unsigned d = (unsigned)(b - a);
-                if (d == 0) { push_start[0] = -1; push_deg[0] = 1; push_val[0] = 1.0; sm.n_push = 1; }
-                else if (1.0 >= P.rmax * (double)d) { push_start[0] = a; push_deg[0] = (int)d; push_val[0] = 1.0 / (double)d; sm.n_push = 1; }
+                // push-list entries [0, BLOCK) live in the tile arrays themselves (off = degree until expand scans it)
+                if (d == 0) { sm.start[0] = -1; sm.off[0] = 1; sm.val[0] = 1.0; sm.n_push = 1; }
+                else if (1.0 >= P.rmax * (double)d) { sm.start[0] = a; sm.off[0] = d; sm.val[0] = 1.0 / (double)d; sm.n_push = 1; }
             }
         }
         __syncthreads();
@@ -406,7 +411,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 unsigned d_push = 0;
                 int start = 0;
                 double val = 0.0;
-                if (j < n_push) { d_push = (unsigned)push_deg[j]; start = push_start[j]; val = push_val[j]; }
+                if (j < n_push) {
+                    if (base == 0) { d_push = sm.off[tid]; start = sm.start[tid]; val = sm.val[tid]; }   // written by settle
+                    else { d_push = (unsigned)push_deg[j]; start = push_start[j]; val = push_val[j]; }
+                }
                 unsigned total;
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
                 sm.off[tid] = excl; sm.start[tid] = start; sm.val[tid] = val;
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     warp_append_multi<kEdgeUnroll>(fresh, P.capS, &sm.n_nxt, err, lpos);
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++)
-                        if (lpos[q] >= 0) nxt_id[lpos[q]] = v[q];
+                        if (lpos[q] >= 0) { if (lpos[q] < kSmallList) sm.fl[lpos[q]] = v[q]; else nxt_id[lpos[q]] = v[q]; }
                 }
                 __syncthreads();
             }
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 for (int q = 0; q < kSettleUnroll; q++) {
                     const int j = base + q * BLOCK + tid;
                     ok[q] = j < n_nxt;
-                    v[q] = ok[q] ? nxt_id[j] : 0;
+                    v[q] = ok[q] ? (j < kSmallList ? sm.fl[j] : nxt_id[j]) : 0;
                 }
                 double x[kSettleUnroll];
                 int pos[kSettleUnroll], hs[kSettleUnroll];
@@ -552,7 +560,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         sup_val[pos[q]] += c * x[q];
                         T.put(v[q], epoch, pos[q], false);
                     }
-                    if (pp[q] >= 0) { push_start[pp[q]] = st[q]; push_deg[pp[q]] = dg[q]; push_val[pp[q]] = val[q]; }
+                    if (pp[q] >= 0) {
+                        if (pp[q] < BLOCK) { sm.start[pp[q]] = st[q]; sm.off[pp[q]] = (unsigned)dg[q]; sm.val[pp[q]] = val[q]; }
+                        else { push_start[pp[q]] = st[q]; push_deg[pp[q]] = dg[q]; push_val[pp[q]] = val[q]; }
+                    }
                 }
             }
             if (DENSE) {
