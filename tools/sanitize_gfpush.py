@@ -8,10 +8,14 @@ indptr, indices = synth.powerlaw_csr(20_000, 200_000, seed=5)
 indptr, indices = indptr.numpy(), indices.numpy()
 src = synth.sources(20_000, 64, seed=4).numpy()
 coef = og.coef_for("ppr", 5, 0.1)
-for kv in (dict(push_smem_hash=2, push_smem_probe=4), dict(push_smem_hash=2, push_smem_probe=1), dict(push_smem_hash=0)):
+"""Small GFPush run for compute-sanitizer (memcheck / racecheck) over every residue-table mode:
+    compute-sanitizer --tool racecheck python tools/sanitize_gfpush.py"""
+for kv in (dict(push_smem_hash=2, push_smem_probe=4), dict(push_smem_hash=2, push_smem_probe=1), dict(push_smem_hash=0),
+           dict(scratch=1)):
+    scratch = kv.pop("scratch", 2)
     for k, v in kv.items(): _lib.set_tuning(k, v)
-    g = propagation.Graph(indptr, indices, 0); g.configure(scratch_mode=2)
+    g = propagation.Graph(indptr, indices, 0); g.configure(scratch_mode=scratch)
     S, K = len(src), 16
     row = np.zeros(S*K, np.int32); col = np.zeros(S*K, np.int32); val = np.zeros(S*K, np.float64)
     g.gfpush_omp(src, row, col, val, coef, 1e-4, K)
-    print(kv, check_topk_rows(indptr, indices, src, coef, 1e-4, K, col, val, row=row, max_rows=32), g.last_stats()['support_total'])
+    print(kv, 'scratch', scratch, check_topk_rows(indptr, indices, src, coef, 1e-4, K, col, val, row=row, max_rows=32), g.last_stats()['support_total'])
