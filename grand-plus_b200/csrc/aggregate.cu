@@ -648,6 +648,7 @@ void dropout_consts(double p, int training, int *use_mask, float *scale, unsigne
 extern "C" {
 
 int gp_aggregate_fwd(const gp_aggregate_args *A, void *stream) {
+    GpRange nvtx_range("gp_aggregate_fwd");
     GP_REQUIRE(A != nullptr, "args is null");
     GP_REQUIRE(A->B >= 0 && A->n_entries >= 0, "negative size");
     GP_REQUIRE(A->F >= 1, "F must be >= 1");
@@ -683,6 +684,7 @@ int gp_aggregate_fwd(const gp_aggregate_args *A, void *stream) {
 }
 
 int gp_aggregate_bwd(const gp_aggregate_bwd_args *A, void *stream) {
+    GpRange nvtx_range("gp_aggregate_bwd");
     GP_REQUIRE(A != nullptr, "args is null");
     GP_REQUIRE(A->B >= 0 && A->n_entries >= 0, "negative size");
     GP_REQUIRE(A->F >= 1, "F must be >= 1");

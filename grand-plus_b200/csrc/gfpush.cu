@@ -1260,6 +1260,7 @@ extern "C" {
 
 int gp_graph_create(const int32_t *indptr, int64_t n_nodes, const int32_t *indices, int64_t nnz, int32_t seed,
                     int device, gp_graph **out) {
+    GpRange nvtx_range("gp_graph_create");
     (void)seed;  // stored and never read by the reference either (graph.h:30,40)
     GP_REQUIRE(out != nullptr, "out is null");
     *out = nullptr;
@@ -1286,6 +1287,7 @@ int gp_graph_create(const int32_t *indptr, int64_t n_nodes, const int32_t *indic
 
 int gp_graph_create_device(const int32_t *d_indptr, int64_t n_nodes, const int32_t *d_indices, int64_t nnz,
                            int device, gp_graph **out) {
+    GpRange nvtx_range("gp_graph_create_device");
     GP_REQUIRE(out != nullptr, "out is null");
     *out = nullptr;
     GP_REQUIRE(d_indptr != nullptr && (d_indices != nullptr || nnz == 0), "null CSR array");
@@ -1328,6 +1330,7 @@ int gp_graph_configure(gp_graph *g, const gp_push_config *cfg) {
 int gp_gfpush_device(gp_graph *g, const int32_t *d_node_idx, int64_t S, const double *coef, int32_t L, double rmax,
                      int32_t K, int32_t *d_row_idx, int32_t *d_col_idx, double *d_value, float *d_value32,
                      void *stream) {
+    GpRange nvtx_range("gp_gfpush_device");
     GP_REQUIRE(g != nullptr, "graph handle is null");
     std::lock_guard<std::mutex> lk(g->mu);
     DeviceGuard guard(g->device);
@@ -1338,6 +1341,7 @@ int gp_gfpush_device(gp_graph *g, const int32_t *d_node_idx, int64_t S, const do
 
 int gp_gfpush(gp_graph *g, const int32_t *node_idx, int64_t S, const double *coef, int32_t L, double rmax, int32_t K,
               int32_t *row_idx, int32_t *col_idx, double *value) {
+    GpRange nvtx_range("gp_gfpush");
     GP_REQUIRE(g != nullptr, "graph handle is null");
     GP_REQUIRE(S >= 0, "negative source count");
     if (S == 0) return GP_OK;

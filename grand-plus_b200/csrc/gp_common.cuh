@@ -7,6 +7,17 @@
 
 #include "../../include/grandplus_b200.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only (dlopens the injection library when a profiler is attached)
+
+// RAII NVTX range around a C-ABI entry point: `ncu --nvtx --nvtx-include "gp_gfpush/"` or an nsys timeline then show the
+// call the kernels belong to (the reference has no tracing hooks at all).
+struct GpRange {
+    explicit GpRange(const char *name) { nvtxRangePushA(name); }
+    ~GpRange() { nvtxRangePop(); }
+    GpRange(const GpRange &) = delete;
+    GpRange &operator=(const GpRange &) = delete;
+};
+
 #ifndef GP_NUM_SMS_FALLBACK
 #define GP_NUM_SMS_FALLBACK 148  // B200: 2 dies x 74 SMs
 #endif
