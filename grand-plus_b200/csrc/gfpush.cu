@@ -34,7 +34,7 @@
 // tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
 int g_push_smem_hash = 1;     // "push_smem_hash": shared-memory residue table in front of the slabs (HBM mode, MODE 2 kernel):
                               // 0 off, 1 auto (on when the expected support is of the order of the table), 2 always on
-int g_push_smem_probe = 4;    // "push_smem_probe": probes before a node is sent to the slab
+int g_push_smem_probe = 2;    // "push_smem_probe": 4-key buckets tried before a node is sent to the slab
 int g_push_hash = 0;          // "push_hash": 1 = route HBM-mode sources through the L2-resident hash tier first
                               // (opt-in: measured slower than the slabs on every BASELINE shape, profiles/r01_hash_tier.md)
 int g_push_cluster = 0;       // "push_cluster": CTAs per source (1,2,4,8,16), 0 = from the pilot statistics
@@ -105,7 +105,7 @@ struct PushParams {
     double *log_val;   // [ctas][capLog]  appended coalesced, merged in shared memory before the top-k
     long long capLog;
     int hslots;        // table slots, power of two
-    int max_probe;     // a node that finds no slot within this many probes goes to the slab for this level
+    int max_probe;     // a node that finds no slot within this many 4-key buckets lives on the slab for this source
 };
 
 enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
@@ -289,7 +289,7 @@ struct Tables {
 // MODE 1: dense next-residue array double[n] in shared memory (small graphs): MODE 2's machinery with slot == node id
 //   (no keys, no probes, no slab residents, a bitmap of reached nodes for the support count).
 // MODE 2: an open-addressed {key, next residue} table in SHARED MEMORY in front of the slabs.  A node that finds a
-//   slot within max_probe probes when the source first touches it lives in the table until the source is done,
+//   slot within max_probe 4-key buckets when the source first touches it lives in the table until the source is done,
 //   every other node lives on the slab (both decisions are stable: entries are never removed while a source is live).
 //   expand: table residents cost a probe and a shared-memory atomic (measured 0.6 edges/clk/SM incl. probing at a
 //           table load of 0.8, profiles/r01_smem_hash_microbench.txt) instead of a DRAM round trip;
@@ -337,14 +337,20 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         claimed = false;
         if (DENSE) return v;
         if (!table_on) return -1;
-        unsigned h = ((unsigned)v * 2654435761u) >> 7 & hmask;
-        for (int probe = 0; probe < P.max_probe; probe++, h = (h + 1) & hmask) {
-            int k = s_keys[h];
-            if (k == -1) {
-                k = atomicCAS(s_keys + h, -1, v);
-                if (k == -1) { claimed = true; return (int)h; }
+        // buckets of four keys (one 16-byte shared-memory read per probe); max_probe buckets are tried
+        unsigned b = (((unsigned)v * 2654435761u) >> 9) & (hmask >> 2);
+        for (int probe = 0; probe < P.max_probe; probe++, b = (b + 1) & (hmask >> 2)) {
+            const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * b);
+            const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                int k = kk[i];
+                if (k == -1) {   // an observed empty is only acted on through the CAS; observed keys are final
+                    k = atomicCAS(s_keys + 4 * b + i, -1, v);
+                    if (k == -1) { claimed = true; return (int)(4 * b + i); }
+                }
+                if (k == v) return (int)(4 * b + i);
             }
-            if (k == v) return (int)h;
         }
         return -1;
     };

@@ -199,7 +199,7 @@ int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, 
  * Aggregation: "agg_kernel" (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf",
  * "agg_max_vec", "agg_max_chunk", "agg_smem_kb".
  * GFPush (HBM mode): "push_smem_hash" (shared-memory residue table in front of the slabs: 0 off, 1 auto from rmax,
- * 2 always), "push_smem_probe" (probes before a node goes to the slab), "push_max_ctas" (cap on persistent CTAs, for
+ * 2 always), "push_smem_probe" (4-key buckets tried before a node goes to the slab), "push_max_ctas" (cap on persistent CTAs, for
  * scaling experiments); the opt-in L2-resident cluster tier: "push_hash" (1 = on), "push_cluster" (CTAs per source:
  * 0 auto, 1, 2, 4, 8, 16), "push_hash_slots", "push_hash_block", "push_l2_mb", "push_load_pct", "push_list_div",
  * "push_pilot", "push_max_clusters".  The same keys are read from the GP_TUNING environment variable

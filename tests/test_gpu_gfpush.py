@@ -203,7 +203,7 @@ class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
     DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
                 "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 1,
-                "push_smem_probe": 4, "push_max_ctas": 0}
+                "push_smem_probe": 2, "push_max_ctas": 0}
 
     def __init__(self, **kv):
         self.kv = kv

@@ -17,7 +17,7 @@ from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
 DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
-            "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 1, "push_smem_probe": 4, "push_max_ctas": 0}
+            "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 1, "push_smem_probe": 2, "push_max_ctas": 0}
 
 
 def main():
