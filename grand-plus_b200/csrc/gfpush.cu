@@ -591,7 +591,19 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             // the residue array is all zero after the last settle: sum the reserve log into it, by slot
             __syncthreads();
             const int n_log = min((long long)sm.n_log, P.capLog);
-            for (int j = tid; j < n_log; j += BLOCK) atomicAdd(s_nxt_dyn + log_id[j], log_val[j]);
+            for (int base = 0; base < n_log; base += BLOCK * 4) {   // four log entries in flight per thread
+                int id[4];
+                double lv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = base + q * BLOCK + tid;
+                    id[q] = j < n_log ? log_id[j] : -1;
+                    lv[q] = j < n_log ? log_val[j] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (id[q] >= 0) atomicAdd(s_nxt_dyn + id[q], lv[q]);
+            }
             __syncthreads();
             GP_PHASE(3);   // reserve merge
         }
