@@ -287,7 +287,7 @@ def run_ours(args):
     h_row, h_col, h_val = pin((S * K,), torch.int32), pin((S * K,), torch.int32), pin((S * K,), torch.float64)
     host_batches = [b.cpu() for b in batches]
     torch.cuda.synchronize(); barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, min(args.steps, 10))
     for i in range(2 + e2e_steps):
         if i == 2:
             torch.cuda.synchronize(); barrier(); torch.cuda.synchronize()
