@@ -87,7 +87,7 @@ struct PushParams {
     int epoch_base;    // slot.epoch == epoch_base + it + 1  <=>  node already in source `it`'s reserve
     int *push_start;   // [ctas][capF]  frontier nodes that passed the threshold: CSR offset (-1 = dangling -> source)
     int *push_deg;     // [ctas][capF]
-    double *push_val;  // [ctas][capF]  r/deg
+    double *push_val;  // [ctas][capF]  residue r (r/deg is taken when the entry is expanded)
     int *nxt_id;       // [ctas][capF]  ids of the next frontier (first-touch order)
     int *sup_id;       // [ctas][capS]  reserve support: node ids ...
     double *sup_val;   // [ctas][capS]  ... and reserve values, compact (first-touch order)
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 const unsigned d = (unsigned)(b - a);
                 // push-list entries [0, BLOCK) live in the tile arrays themselves (off = degree until expand scans it)
                 if (d == 0) { sm.start[0] = -1; sm.off[0] = 1; sm.val[0] = 1.0; sm.n_push = 1; }
-                else if (1.0 >= P.rmax * (double)d) { sm.start[0] = a; sm.off[0] = d; sm.val[0] = 1.0 / (double)d; sm.n_push = 1; }
+                else if (1.0 >= P.rmax * (double)d) { sm.start[0] = a; sm.off[0] = d; sm.val[0] = 1.0; sm.n_push = 1; }
             }
         }
         __syncthreads();
@@ -420,6 +420,9 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 if (j < n_push) {
                     if (base == 0) { d_push = sm.off[tid]; start = sm.start[tid]; val = sm.val[tid]; }   // written by settle
                     else { d_push = (unsigned)push_deg[j]; start = push_start[j]; val = push_val[j]; }
+                    // the push list carries the residue; r/deg (graph.h:95) is taken here, one fp64 division per ENTRY with every
+                    // lane busy, instead of in settle where a few pushing lanes made whole warps walk the division
+                    val = val / (double)d_push;
                 }
                 unsigned total;
                 const unsigned excl = gp_block_exclusive_scan<BLOCK>(d_push, sm.warp_scan, total);
@@ -547,7 +550,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         const unsigned d = (unsigned)(b[q] - a[q]);
                         if (d == 0) push[q] = true;                                   // graph.h:91-93: back to the source
                         else if (x[q] >= P.rmax * (double)d) {                        // graph.h:94
-                            push[q] = true; st[q] = a[q]; dg[q] = (int)d; val[q] = x[q] / (double)d;  // graph.h:95
+                            push[q] = true; st[q] = a[q]; dg[q] = (int)d;   // val stays the residue: r/deg (graph.h:95) is taken in expand
                         }
                     }
                 }
