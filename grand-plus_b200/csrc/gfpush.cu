@@ -9,18 +9,22 @@
 // B200 design (not the reference's per-thread unordered_maps):
 //   * persistent CTAs (SM count x resident CTAs), sources handed out through one global atomic
 //     counter -- the schedule(dynamic) of graph.h:73, so hub-heavy sources do not stall a wave;
-//   * per-CTA DIRECT-ADDRESSED tables instead of hash maps: `nxt[n]` (next-level residue, fp64,
-//     accumulated with native fp64 atomics) and `rsv[n]` (reserve, fp64).  180 GB of HBM makes a
-//     perfect hash (node id -> slot) affordable for every BASELINE config, which removes all
-//     probing; small graphs put `nxt` in shared memory instead (scratch mode SMEM);
-//   * frontiers are compact (id, value) lists; a node joins the next frontier when its atomicAdd
-//     returns 0.0 (first touch), so tables are cleared by walking lists, never by memset;
+//   * the next-level residues of a source live ON CHIP whenever its support allows: a dense fp64 array in shared
+//     memory for small graphs (MODE 1), a 16 384-slot open-addressed {key, residue} table in the 227 KB of shared
+//     memory for supports of that order (MODE 2); what does not fit -- single nodes in MODE 2, everything for
+//     supports of 10^5 nodes (MODE 0) -- goes to per-CTA DIRECT-ADDRESSED slabs in HBM (16-byte slots
+//     {residue, epoch, reserve position}: a perfect hash node id -> slot, no probing, never reset);
+//   * the reserve of on-chip residents is APPENDED as (slot, coef * residue) pairs to a coalesced log and summed by
+//     slot into the (then all-zero) residue array after the last level; slab residents keep compact support arrays;
+//   * frontiers are compact lists; a node joins the next frontier when its atomic add returns 0.0 (first touch),
+//     so tables are cleared by walking lists, never by memset;
 //   * edge-balanced expansion: a CTA tile of BLOCK frontier nodes is prefix-summed by degree and
 //     the tile's edges are dealt to threads by rank, so a 240K-degree hub is expanded by the whole
 //     CTA with coalesced `indices` reads and degree-1 leaves do not idle a warp each;
 //   * top-k is an MSD radix select on the fp64 bit pattern (11-bit digits, exponent first),
 //     finished by rank-counting the single boundary bucket in shared memory.
 //   Residues stay fp64 end to end (the threshold test r >= rmax*deg is a hard comparison).
+//   Measured history, rooflines and the designs that lost: DESIGN.md 4.1, profiles/r01_hash_tier.md.
 #include "gp_common.cuh"
 
 #include <cooperative_groups.h>
