@@ -20,7 +20,7 @@
 #include <algorithm>
 #include <string>
 
-extern int g_push_hash, g_push_cluster, g_push_hash_slots, g_push_l2_mb, g_push_load_pct, g_push_list_div, g_push_pilot, g_push_hash_block, g_push_max_clusters, g_push_smem_hash, g_push_smem_probe, g_push_max_ctas,
+extern int g_push_cluster, g_push_cluster_probe, g_push_hub_deg, g_push_max_clusters, g_push_smem_hash, g_push_smem_probe, g_push_max_ctas,
     g_push_tuning_gen;  // gfpush.cu
 
 namespace {
@@ -738,24 +738,17 @@ int gp_set_tuning(const char *key, int64_t value) {
     else if (k == "agg_max_vec") g_agg_max_vec = (int)value;
     else if (k == "agg_max_chunk") g_agg_max_chunk = (int)value;
     else if (k == "agg_smem_kb") g_agg_smem_kb = (int)value;
-    else if (k == "push_hash") { g_push_hash = (int)value; g_push_tuning_gen++; }
     else if (k == "push_cluster") {
-        GP_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "push_cluster must be 0, 1, 2, 4, 8 or 16");
+        GP_REQUIRE(value == -1 || value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16,
+                   "push_cluster must be 0 (off), 1 (auto), -1 (one CTA per source), 2, 4, 8 or 16");
         g_push_cluster = (int)value; g_push_tuning_gen++;
     }
-    else if (k == "push_hash_slots") {
-        GP_REQUIRE(value == 0 || (value >= 2048 && value <= (1ll << 30)), "push_hash_slots must be 0 (auto) or in [2048, 2^30]");
-        g_push_hash_slots = (int)value; g_push_tuning_gen++;
-    }
-    else if (k == "push_l2_mb") { GP_REQUIRE(value >= 1, "push_l2_mb must be positive"); g_push_l2_mb = (int)value; g_push_tuning_gen++; }
-    else if (k == "push_load_pct") { GP_REQUIRE(value >= 10 && value <= 85, "push_load_pct must be in [10, 85]"); g_push_load_pct = (int)value; g_push_tuning_gen++; }
-    else if (k == "push_list_div") { GP_REQUIRE(value >= 1, "push_list_div must be >= 1"); g_push_list_div = (int)value; g_push_tuning_gen++; }
-    else if (k == "push_hash_block") { GP_REQUIRE(value == 512 || value == 1024, "push_hash_block must be 512 or 1024"); g_push_hash_block = (int)value; g_push_tuning_gen++; }
+    else if (k == "push_cluster_probe") { GP_REQUIRE(value >= 1 && value <= 4096, "push_cluster_probe must be in [1, 4096]"); g_push_cluster_probe = (int)value; }
+    else if (k == "push_hub_deg") { GP_REQUIRE(value >= 0, "push_hub_deg must be >= 0"); g_push_hub_deg = (int)value; g_push_tuning_gen++; }
     else if (k == "push_max_clusters") { GP_REQUIRE(value >= 0, "push_max_clusters must be >= 0"); g_push_max_clusters = (int)value; g_push_tuning_gen++; }
     else if (k == "push_smem_hash") { g_push_smem_hash = (int)value; g_push_tuning_gen++; }
     else if (k == "push_smem_probe") { GP_REQUIRE(value >= 1 && value <= 1024, "push_smem_probe must be in [1, 1024]"); g_push_smem_probe = (int)value; }
     else if (k == "push_max_ctas") { GP_REQUIRE(value >= 0, "push_max_ctas must be >= 0"); g_push_max_ctas = (int)value; }
-    else if (k == "push_pilot") { GP_REQUIRE(value >= 1, "push_pilot must be >= 1"); g_push_pilot = (int)value; g_push_tuning_gen++; }
     else { gp_set_error("unknown tuning key '%s'", key); return GP_ERR_INVALID; }
     return GP_OK;
 }

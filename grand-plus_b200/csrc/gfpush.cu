@@ -26,6 +26,8 @@
 //   Residues stay fp64 end to end (the threshold test r >= rmax*deg is a hard comparison).
 //   Measured history, rooflines and the designs that lost: DESIGN.md 4.1, profiles/r01_hash_tier.md.
 #include "gp_common.cuh"
+#include "gfpush_shared.cuh"
+#include "gfpush_cluster.h"
 
 #include <cooperative_groups.h>
 
@@ -35,29 +37,22 @@
 #include <new>
 #include <vector>
 
-// tuning knobs (gp_set_tuning): the L2-resident hash tier of HBM-mode GFPush
+// tuning knobs (gp_set_tuning)
 int g_push_smem_hash = 1;     // "push_smem_hash": shared-memory residue table in front of the slabs (HBM mode, MODE 2 kernel):
                               // 0 off, 1 auto (on when the expected support is of the order of the table), 2 always on
 int g_push_smem_probe = 2;    // "push_smem_probe": 4-key buckets tried before a node is sent to the slab
-int g_push_hash = 0;          // "push_hash": 1 = route HBM-mode sources through the L2-resident hash tier first
-                              // (opt-in: measured slower than the slabs on every BASELINE shape, profiles/r01_hash_tier.md)
-int g_push_cluster = 0;       // "push_cluster": CTAs per source (1,2,4,8,16), 0 = from the pilot statistics
-int g_push_hash_slots = 0;    // "push_hash_slots": table capacity per cluster, 0 = from the pilot statistics
-int g_push_l2_mb = 48;        // "push_l2_mb": L2 budget the live tables should fit
-int g_push_load_pct = 60;     // "push_load_pct": (support bound)/(table size) the per-level sizing aims at
-int g_push_list_div = 8;      // "push_list_div": levels with fewer than C/list_div edges settle via the first-touch list
-int g_push_hash_block = 1024; // "push_hash_block": threads per CTA of the hash tier (512 or 1024)
-int g_push_max_clusters = 0;  // "push_max_clusters": cap on concurrently processed sources of the hash tier (0 = all SMs)
+int g_push_cluster = 1;       // "push_cluster": the cluster kernel (gfpush_cluster.cu) for graphs beyond the dense shared-memory mode:
+                              // 0 off, 1 auto (cluster size from the expected support), 2/4/8/16 = that cluster size, -1 = one CTA
+int g_push_cluster_probe = 8; // "push_cluster_probe": 4-key buckets tried before a source is handed to the slab kernel
+int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree are expanded by the whole cluster (0 = 64 x G)
+int g_push_max_clusters = 0;  // "push_max_clusters": cap on the resident clusters (0 = all the device schedules); scaling experiments
 int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments
-int g_push_pilot = 256;       // "push_pilot": sources pushed on the slabs to measure the support before choosing G
 int g_push_tuning_gen = 0;    // bumped by gp_set_tuning so that handles re-plan
+
+using namespace gpp;
 
 namespace {
 
-constexpr int kHistBins = 2048;     // 11-bit radix digits
-constexpr int kBucketCap = 512;     // boundary bucket resolved in shared memory
-constexpr int kMaxK = kBucketCap;   // K above this is refused
-constexpr int kMaxLevels = 256;
 constexpr int kEdgeUnroll = 4;
 constexpr int kSettleUnroll = 4;
 constexpr int kSmallList = kHistBins;   // frontier-list entries kept in shared memory (the rest go to HBM)
@@ -99,7 +94,7 @@ struct PushParams {
     unsigned long long *queue;  // [1] next source
     unsigned long long *stats;  // [0] edges [1] frontier [2] support [3] error flags
     unsigned long long *cum;    // [0] edges [1] frontier [2] support [3] sources; never reset by a call
-    // redo mode (second pass after gfpush_hash_kernel): the queue indexes redo[0 .. *redo_count)
+    // redo mode (second pass after gfpush_cluster_kernel): the queue indexes redo[0 .. *redo_count)
     const int *redo;
     const unsigned long long *redo_count;
     unsigned long long *max_support;  // largest reserve support of any source of this launch (pilot statistics)
@@ -111,8 +106,6 @@ struct PushParams {
     int hslots;        // table slots, power of two
     int max_probe;     // a node that finds no slot within this many 4-key buckets lives on the slab for this source
 };
-
-enum : unsigned long long { kErrOverflow = 1ull, kErrBadSource = 2ull };
 
 template <int BLOCK>
 struct PushSmem {
@@ -184,51 +177,6 @@ __device__ __forceinline__ void warp_append_multi(const bool (&is_new)[U], long 
     }
 }
 
-// Largest t in [0, BLOCK) with off[t] <= e (off is a non-decreasing exclusive scan, off[0] == 0).
-template <int BLOCK>
-__device__ __forceinline__ int owner_of_edge(const unsigned *off, unsigned e) {
-    int lo = 0;
-#pragma unroll
-    for (int step = BLOCK / 2; step >= 1; step >>= 1) {
-        const int mid = lo + step;
-        if (off[mid] <= e) lo = mid;   // mid <= BLOCK-1 always: lo + step never exceeds BLOCK-1
-    }
-    return lo;
-}
-
-// Finds the radix bin holding the kk-th largest among `hist` (bins ordered ascending by key).
-// Results in *sel_bin / *sel_above (count in strictly higher bins) / *sel_inbin; returns total.
-// Every thread of the CTA must call it (block scan inside).
-template <int BLOCK>
-__device__ __forceinline__ unsigned select_bin_generic(const unsigned *hist, unsigned *warp_scan, int nbins, int kk,
-                                                       bool kk_is_cap, int *sel_bin, int *sel_above, int *sel_inbin) {
-    // thread t owns bins [hi - per + 1, hi], hi = nbins-1 - t*per, walking from the top
-    const int per = (nbins + BLOCK - 1) / BLOCK;
-    const int tid = threadIdx.x;
-    unsigned local = 0;
-    const int hi = nbins - 1 - tid * per;
-#pragma unroll 4
-    for (int i = 0; i < per; i++) {
-        int b = hi - i;
-        if (b >= 0) local += hist[b];
-    }
-    unsigned total;
-    unsigned above = gp_block_exclusive_scan<BLOCK>(local, warp_scan, total);
-    unsigned want = kk_is_cap ? min((unsigned)kk, total) : (unsigned)kk;
-    if (want > 0 && above < want && want <= above + local) {
-        unsigned acc = above;
-        for (int i = 0; i < per; i++) {
-            int b = hi - i;
-            if (b < 0) break;
-            unsigned h = hist[b];
-            if (acc + h >= want) { *sel_bin = b; *sel_above = (int)acc; *sel_inbin = (int)h; break; }
-            acc += h;
-        }
-    }
-    if (want == 0 && tid == 0) { *sel_bin = -1; *sel_above = 0; *sel_inbin = 0; }
-    __syncthreads();
-    return total;
-}
 template <int BLOCK>
 __device__ __forceinline__ unsigned select_bin(PushSmem<BLOCK> &sm, int nbins, int kk, bool kk_is_cap) {
     return select_bin_generic<BLOCK>(sm.hist, sm.warp_scan, nbins, kk, kk_is_cap, &sm.sel_bin, &sm.sel_above, &sm.sel_inbin);
@@ -498,6 +446,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             // Every node of the new frontier, independently: take its residue, credit the reserve,
             // and decide now whether it will push at the next level.
             const int n_nxt = min((long long)sm.n_nxt, P.capF);
+            if (tid == 0 && (long long)sm.n_nxt > P.capF) atomicOr(err, kErrOverflow);   // never silent
             const int next_level = level + 1;
             const bool will_push = next_level < P.L - 1;
             const double c = P.coef[next_level];
@@ -747,16 +696,6 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
 }
 
 #undef GP_PHASE
-#include "gfpush_hash.cuh"
-
-// Hash-tier invariant between sources: every key empty, residues and reserves zero.
-__global__ void init_hash_kernel(int *keys, double *nxt, double *rsv, long long n_slots) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += stride) {
-        keys[i] = kEmptyKey; nxt[i] = 0.0; rsv[i] = 0.0;
-    }
-}
-
 // Table invariant between sources: next residue 0; epoch 0 never matches a source (epochs start at 1).
 __global__ void init_tables_kernel(int4 *tab16, int2 *meta8, long long n_slots) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -808,21 +747,18 @@ struct gp_graph {
     long long scratch_capLog = 0;
     long long epoch_base = 0;              // sources pushed since the tables were last initialised
     double *d_coef = nullptr;              // [kMaxLevels]
-    // [0] queue [1..4] stats [5] hash-tier queue [6] redo count [7] redo queue [8] max support | [16..21] cumulative
+    // [0] queue [1..3] stats [4] error flags (sticky until read) [6] redo count [7] slab-kernel queue [8] max support
+    // | [16..21] cumulative | [24..31] phase cycles
     unsigned long long *d_ctrl = nullptr;
-    // hash tier (HBM mode): chosen once per (L, rmax, coef) from a pilot run on the slabs
-    struct Tier {
-        bool valid = false, enabled = false;
-        int gen = -1, L = 0;
-        double rmax = 0.0, coef_sum = 0.0, coef0 = 0.0;
-        double avg_support = 0.0;
-        long long max_support = 0;
-        int G = 1, clusters = 0, Cmax = 0, block = 1024;
-        long long capP = 0, capL = 0;
-        size_t off_keys = 0, off_nxt = 0, off_rsv = 0, off_ps = 0, off_pd = 0, off_pv = 0, off_nid = 0, off_tk = 0, off_tv = 0;
-    } tier;
-    void *hscratch = nullptr;
-    size_t hscratch_bytes = 0;
+    // cluster kernel (gfpush_cluster.cu): CSR entries with the degree code, per-CTA / per-cluster scratch
+    int *d_packed = nullptr;
+    int idbits = 32;
+    void *cscratch = nullptr;
+    size_t cscratch_bytes = 0;
+    int max_clusters[5] = {-1, -1, -1, -1, -1};   // resident clusters of 1, 2, 4, 8, 16 CTAs (-1 = not asked yet)
+    // orders a push after the previous one on this handle when the two run on different streams
+    cudaEvent_t ev_done = nullptr;
+    bool ev_recorded = false;
     int *d_redo = nullptr;
     size_t d_redo_cap = 0;
     // staging for the host-buffer entry point
@@ -862,7 +798,7 @@ struct Plan {
     int hslots;  // > 0: MODE 2 (shared-memory hash in front of the slabs)
 };
 
-int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
+int make_plan(gp_graph *g, long long S, int L, double rmax, bool redo_only, Plan *pl) {
     const long long n = g->n;
     // Measured on B200 (profiles/r01_block_sweep.md): one 1024-thread CTA per SM wins whenever a source
     // carries thousands of frontier nodes (fewer concurrent sources -> their table lines stay in L2);
@@ -897,13 +833,15 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         per_sm = std::min(per_sm, fit);
     }
     long long ctas = (long long)g->num_sms * per_sm;  // scratch is sized for a full grid; small calls launch fewer
+    // behind the cluster kernel the slabs only take the few sources it hands over: a quarter of the SMs, no table
+    if (redo_only) ctas = std::max<long long>(1, ctas / 4);
     // MODE 2: the largest power-of-two table {int key, double residue} that fits beside the static shared memory
     int hslots = 0;
     // The table pays when a source's support is of the order of the table (measured on B200, profiles/r01_hash_tier.md);
     // supports of the BASELINE shapes are 0.13 - 0.19 / rmax (Reddit 12.9 K @1e-5, MAG 18.7 K @1e-5, Amazon2M 152 K
     // @1e-6), so "auto" (1) keeps the plain slabs when 0.15 / rmax is beyond twice the largest table; 2 forces it on.
     if (mode == GP_SCRATCH_SMEM) hslots = (int)n;   // MODE 1: slot == node id
-    bool want_table = mode == GP_SCRATCH_HBM && g_push_smem_hash != 0;
+    bool want_table = mode == GP_SCRATCH_HBM && g_push_smem_hash != 0 && !redo_only;
     if (want_table && g_push_smem_hash == 1 && rmax > 0.0 && std::min(0.15 / rmax, (double)n) > 2.0 * 16384.0) want_table = false;
     if (want_table && g_push_smem_hash == 1 && rmax <= 0.0 && n > 2 * 16384) want_table = false;
     if (want_table) {
@@ -915,7 +853,8 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, Plan *pl) {
         }
     }
     // reserve log of MODE 2: at most one entry per table slot per level
-    const long long capLog = hslots ? (long long)std::max(L, 1) * hslots + 8192 : 0;
+    // (a level logs at most min(slots, capF) entries)
+    const long long capLog = hslots ? std::min((long long)std::max(L, 1) * hslots, 1 + (long long)std::max(L - 1, 0) * capF) + 8192 : 0;
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
         p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 0), 256);
@@ -995,132 +934,89 @@ int launch_push(const PushParams &P, const Plan &pl, cudaStream_t stream) {
     return GP_OK;
 }
 
-// ---- hash tier: launch helpers -------------------------------------------------------------------
-template <int BLOCK, bool MULTI>
-int hash_launch_config(int G, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, cudaStream_t stream) {
-    auto kernel = gfpush_hash_kernel<BLOCK, MULTI>;
-    if (G > 8) GP_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    *cfg = cudaLaunchConfig_t{};
-    cfg->blockDim = dim3(BLOCK); cfg->gridDim = dim3((unsigned)G); cfg->dynamicSmemBytes = 0; cfg->stream = stream;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg->attrs = attr; cfg->numAttrs = MULTI ? 1 : 0;
-    return GP_OK;
-}
-
-// How many clusters of G CTAs the device keeps resident.
-template <int BLOCK>
-int hash_max_clusters_t(gp_graph *g, int G, int *out) {
-    int per_sm = 0;
-    if (G == 1) {
-        GP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gfpush_hash_kernel<BLOCK, false>, BLOCK, 0));
-        *out = g->num_sms * std::max(per_sm, 1);
-        return GP_OK;
-    }
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    int rc = hash_launch_config<BLOCK, true>(G, &cfg, attr, nullptr);
-    if (rc != GP_OK) return rc;
-    cfg.gridDim = dim3((unsigned)(g->num_sms / G * G));
-    int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gfpush_hash_kernel<BLOCK, true>, &cfg);
-    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
-    *out = n;
-    return GP_OK;
-}
-int hash_max_clusters(gp_graph *g, int block, int G, int *out) {
-    return block == 512 ? hash_max_clusters_t<512>(g, G, out) : hash_max_clusters_t<1024>(g, G, out);
-}
-
-template <int BLOCK>
-int launch_hash_t(const HashParams &P, int G, int clusters, cudaStream_t stream) {
-    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
-    if (G == 1) {
-        gfpush_hash_kernel<BLOCK, false><<<(unsigned)clusters, BLOCK, 0, stream>>>(P);
-    } else {
-        int rc = hash_launch_config<BLOCK, true>(G, &cfg, attr, stream);
-        if (rc != GP_OK) return rc;
-        cfg.gridDim = dim3((unsigned)(clusters * G));
-        GP_CUDA_TRY(cudaLaunchKernelEx(&cfg, gfpush_hash_kernel<BLOCK, true>, P));
-    }
-    GP_CUDA_TRY(cudaGetLastError());
-    return GP_OK;
-}
-int launch_hash(const HashParams &P, int block, int G, int clusters, cudaStream_t stream) {
-    return block == 512 ? launch_hash_t<512>(P, G, clusters, stream) : launch_hash_t<1024>(P, G, clusters, stream);
-}
-
-// Chooses cluster size and table capacity from the pilot's support statistics and allocates the tier.
-int plan_tier(gp_graph *g, const Plan &pl, double avg_support, long long max_support, cudaStream_t stream) {
-    gp_graph::Tier &t = g->tier;
-    t.avg_support = avg_support; t.max_support = max_support;
-    t.enabled = false;
-    t.block = g_push_hash_block == 512 ? 512 : 1024;
-    const long long n = g->n;
-    // table capacity: twice the largest pilot support at the target load, never more than the graph needs
-    long long cmax = g_push_hash_slots > 0 ? g_push_hash_slots
-                                           : (long long)std::ceil(2.0 * (double)std::max<long long>(max_support, 256) * 100.0 / g_push_load_pct);
-    const long long cap_n = (long long)std::ceil((double)n * 100.0 / g_push_load_pct) + 1024;
-    cmax = std::min(cmax, cap_n);
-    cmax = std::max<long long>((cmax + 1023) / 1024 * 1024, 2048);
-    if (cmax > (1ll << 30)) return GP_OK;
-    // live bytes per source: 20 B per slot at a typical 55 % fill of the bound-sized table, plus the lists
-    const double live = 36.0 * std::max(avg_support, 64.0) + 16384.0;
-    const double budget = (double)g_push_l2_mb * 1048576.0;
-    int G = g_push_cluster, clusters = 0;
-    if (G == 0) {
-        const int cand[5] = {1, 2, 4, 8, 16};
-        int best = 0, best_clusters = 0;
-        for (int c : cand) {
-            int nc = 0;
-            int rc = hash_max_clusters(g, t.block, c, &nc);
-            if (rc != GP_OK) return rc;
-            if (nc <= 0) continue;
-            best = c; best_clusters = nc;
-            if ((double)nc * live <= budget) break;
-        }
-        G = best; clusters = best_clusters;
-        // a table per source that is not smaller than the slab buys nothing
-        if (G == 0 || cmax * 20 >= n * 16) return GP_OK;
-    } else {
-        GP_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8 || G == 16, "push_cluster must be 0, 1, 2, 4, 8 or 16");
-        int rc = hash_max_clusters(g, t.block, G, &clusters);
-        if (rc != GP_OK) return rc;
-        GP_REQUIRE(clusters > 0, "a cluster of %d CTAs x 1024 threads is not schedulable on this device", G);
-    }
-    if (g_push_max_clusters > 0) clusters = std::min(clusters, g_push_max_clusters);
-    t.G = G; t.clusters = clusters; t.Cmax = (int)cmax;
-    t.capP = std::min<long long>(pl.capF, cmax);
-    t.capL = cmax / std::max(g_push_list_div, 1) + 1024;
-    size_t o = 0;
-    const size_t c = (size_t)clusters;
-    t.off_keys = o; o += align_up(c * cmax * 4, 256);
-    t.off_nxt = o; o += align_up(c * cmax * 8, 256);
-    t.off_rsv = o; o += align_up(c * cmax * 8, 256);
-    t.off_ps = o; o += align_up(c * t.capP * 4, 256);
-    t.off_pd = o; o += align_up(c * t.capP * 4, 256);
-    t.off_pv = o; o += align_up(c * t.capP * 8, 256);
-    t.off_nid = o; o += align_up(c * t.capL * 4, 256);
-    t.off_tk = o; o += align_up(c * cmax * 4, 256);
-    t.off_tv = o; o += align_up(c * cmax * 8, 256);
-    if (g->hscratch_bytes < o) {
-        GP_CUDA_TRY(cudaStreamSynchronize(stream));
-        cudaFree(g->hscratch); g->hscratch = nullptr; g->hscratch_bytes = 0;
-        cudaError_t e = cudaMalloc(&g->hscratch, o);
-        if (e != cudaSuccess) { cudaGetLastError(); return GP_OK; }  // no room: stay on the slabs
-        g->hscratch_bytes = o;
-    }
-    char *hb = (char *)g->hscratch;
-    init_hash_kernel<<<g->num_sms * 8, 256, 0, stream>>>((int *)(hb + t.off_keys), (double *)(hb + t.off_nxt),
-                                                         (double *)(hb + t.off_rsv), (long long)clusters * cmax);
-    GP_CUDA_TRY(cudaGetLastError());
-    t.enabled = true;
-    return GP_OK;
-}
-
 int launch_slab(const PushParams &P, const Plan &pl, cudaStream_t stream) {
     return pl.block == 256 ? launch_push<256>(P, pl, stream)
            : pl.block == 512 ? launch_push<512>(P, pl, stream)
                              : launch_push<1024>(P, pl, stream);
+}
+
+// ---- cluster kernel: planning ------------------------------------------------------------------------
+struct ClusterPlan {
+    int G = 0, clusters = 0, hub_min_deg = 0;
+    long long capP = 0, capX = 0;
+    int capHub = 0;
+    size_t bytes = 0;
+    size_t off_ps = 0, off_pl = 0, off_pa = 0, off_xi = 0, off_xv = 0, off_ci = 0, off_cv = 0, off_hs = 0, off_hd = 0, off_ha = 0;
+};
+
+int cluster_slot_of(int G) { return G == 1 ? 0 : G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : 4; }
+
+// Chooses the cluster size for this call (0 = use the per-CTA kernels) and sizes its scratch.
+int plan_cluster(gp_graph *g, long long S, int L, double rmax, int K, long long capF, ClusterPlan *cp) {
+    *cp = ClusterPlan{};
+    if (g_push_cluster == 0) return GP_OK;
+    const long long n = g->n;
+    // supports of the BASELINE shapes are 0.13 - 0.19 / rmax (Reddit 13.2 K @1e-5, MAG 18.8 K @1e-5, Amazon2M 152 K @1e-6);
+    // a CTA's 16 384-slot table is kept below a load of ~0.6 for the typical source, outliers go to the slab kernel
+    const double est = rmax > 0.0 ? std::min(0.15 / rmax, (double)n) : (double)n;
+    int G = 0;
+    if (g_push_cluster == 1) {
+        for (int c = 1; c <= kClusterMaxG; c *= 2)
+            if (est / c <= 0.6 * kClusterSlots) { G = c; break; }
+        if (G == 0) return GP_OK;   // beyond 16 CTAs: the slabs take it
+    } else {
+        G = g_push_cluster < 0 ? 1 : g_push_cluster;
+    }
+    int &mc = g->max_clusters[cluster_slot_of(G)];
+    if (mc < 0) {
+        int rc = gpc_max_clusters(G, g->num_sms, &mc);
+        if (rc != GP_OK) return rc;
+    }
+    if (mc <= 0) {
+        GP_REQUIRE(g_push_cluster == 1, "clusters of %d CTAs cannot be scheduled on this device", G);
+        return GP_OK;
+    }
+    int clusters = mc;
+    if (g_push_max_clusters > 0) clusters = std::min(clusters, g_push_max_clusters);
+    clusters = (int)std::min<long long>(clusters, S);
+    cp->G = G; cp->clusters = clusters;
+    cp->hub_min_deg = g_push_hub_deg > 0 ? g_push_hub_deg : 64 * G;
+    cp->capP = capF;
+    // a level pushes at most capF edges; hashed ownership spreads them evenly over the G x G streams of a cluster
+    cp->capX = G == 1 ? 1 : std::min<long long>(capF, std::max<long long>(4096, 8 * capF / ((long long)G * G)));
+    // a pushing node of degree d carries r >= rmax * d, and a level's residues sum to <= 1
+    double hub = rmax > 0.0 ? std::ceil(1.0 / (rmax * cp->hub_min_deg)) + 16.0 : (double)n;
+    cp->capHub = G == 1 ? 1 : (int)std::min<double>(hub, (double)std::min<long long>(n, 1ll << 24));
+    const size_t ctas = (size_t)clusters * G;
+    size_t o = 0;
+    cp->off_ps = o; o += align_up(ctas * cp->capP * 4, 256);
+    cp->off_pl = o; o += align_up(ctas * cp->capP * 4, 256);
+    cp->off_pa = o; o += align_up(ctas * cp->capP * 8, 256);
+    cp->off_xi = o; o += align_up(ctas * G * cp->capX * 4, 256);
+    cp->off_xv = o; o += align_up(ctas * G * cp->capX * 8, 256);
+    cp->off_ci = o; o += align_up(ctas * K * 4, 256);
+    cp->off_cv = o; o += align_up(ctas * K * 8, 256);
+    cp->off_hs = o; o += align_up((size_t)clusters * cp->capHub * 4, 256);
+    cp->off_hd = o; o += align_up((size_t)clusters * cp->capHub * 4, 256);
+    cp->off_ha = o; o += align_up((size_t)clusters * cp->capHub * 8, 256);
+    cp->bytes = o;
+    return GP_OK;
+}
+
+// CSR entries with the degree code in the spare high bits (built once per handle, on first use).
+int ensure_packed(gp_graph *g, cudaStream_t stream) {
+    if (g->d_packed) return GP_OK;
+    int idbits = 1;
+    while (idbits < 32 && (1ll << idbits) < g->n) idbits++;
+    if (32 - idbits < 3) idbits = 32;   // fewer than 3 spare bits: no code, the node record is always fetched
+    cudaError_t e = cudaMalloc(&g->d_packed, sizeof(int) * (size_t)std::max<long long>(g->nnz, 1));
+    if (e != cudaSuccess) { gp_set_error("cudaMalloc of the packed CSR failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return GP_ERR_NOMEM; }
+    g->idbits = idbits;
+    if (idbits == 32) {
+        GP_CUDA_TRY(cudaMemcpyAsync(g->d_packed, g->d_indices, sizeof(int) * (size_t)g->nnz, cudaMemcpyDeviceToDevice, stream));
+        return GP_OK;
+    }
+    return gpc_pack_indices(g->d_node_rec, g->d_indices, g->nnz, idbits, g->d_packed, g->num_sms, stream);
 }
 
 int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const double *coef, int L, double rmax,
@@ -1133,13 +1029,27 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     g->last = gp_push_stats{};
     if (S == 0) return GP_OK;
     GP_REQUIRE(d_node_idx && d_row && d_col && d_val, "null device buffer");
+    // Every push on a handle shares the control block, the coefficient array and the scratch: a push on another stream
+    // (gp_gfpush runs on the handle's own stream, gp_gfpush_device on the caller's) waits for the previous one.
+    if (g->ev_recorded) GP_CUDA_TRY(cudaStreamWaitEvent(stream, g->ev_done, 0));
     Plan pl{};
-    int rc = make_plan(g, S, L, rmax, &pl);
+    int rc = make_plan(g, S, L, rmax, false, &pl);
     if (rc != GP_OK) return rc;
+    ClusterPlan cp{};
+    if (pl.mode == GP_SCRATCH_HBM) {
+        rc = plan_cluster(g, S, L, rmax, K, pl.capF, &cp);
+        if (rc != GP_OK) return rc;
+        if (cp.G > 0) {   // the slabs only back the cluster kernel up
+            rc = make_plan(g, S, L, rmax, true, &pl);
+            if (rc != GP_OK) return rc;
+        }
+    }
     rc = ensure_scratch(g, pl, S, stream);
     if (rc != GP_OK) return rc;
     GP_CUDA_TRY(cudaMemcpyAsync(g->d_coef, coef, sizeof(double) * L, cudaMemcpyHostToDevice, stream));
-    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 16, stream));
+    // the error word [4] is sticky until collect_stats reads it
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long) * 4, stream));
+    GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl + 5, 0, sizeof(unsigned long long) * 11, stream));
     char *base = (char *)g->scratch;
     PushParams P{};
     P.indptr = g->d_indptr; P.node_rec = g->d_node_rec; P.indices = g->d_indices; P.n = (int)g->n;
@@ -1154,91 +1064,59 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     P.sup_id = (int *)(base + pl.off_sup_id);
     P.sup_val = (double *)(base + pl.off_cand);
     P.capF = pl.capF; P.capS = pl.capS;
-    P.queue = g->d_ctrl; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 16;
+    P.queue = g->d_ctrl + 7; P.stats = g->d_ctrl + 1; P.cum = g->d_ctrl + 16;
     P.max_support = g->d_ctrl + 8; P.phase = g->d_ctrl + 24;
     P.log_id = (int *)(base + pl.off_log_id); P.log_val = (double *)(base + pl.off_log_val); P.capLog = pl.capLog;
     P.hslots = pl.hslots; P.max_probe = std::max(g_push_smem_probe, 1);
     P.redo = nullptr; P.redo_count = nullptr;
     int launches = 0;
-    long long done = 0;  // sources [0, done) are finished by the pilot
-
-    // ---- tier choice (HBM mode only): pilot on the slabs once per (L, rmax, coef) and tuning generation
-    const bool want_hash = pl.mode == GP_SCRATCH_HBM && g_push_hash != 0;
-    if (want_hash) {
-        double csum = 0.0;
-        for (int i = 0; i < L; i++) csum += coef[i] * (double)(i + 1);
-        gp_graph::Tier &t = g->tier;
-        const bool same = t.valid && t.gen == g_push_tuning_gen && t.L == L && t.rmax == rmax && t.coef_sum == csum &&
-                          t.coef0 == coef[0];
-        if (!same) {
-            const long long pilot = std::min<long long>(S, std::max(g_push_pilot, 1));
-            if (S >= 2 * pilot) {
-                PushParams Q = P;
-                Q.S = pilot;
-                rc = launch_slab(Q, pl, stream);
-                if (rc != GP_OK) return rc;
-                launches++;
-                unsigned long long h[9];
-                GP_CUDA_TRY(cudaMemcpyAsync(h, g->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, stream));
-                GP_CUDA_TRY(cudaStreamSynchronize(stream));
-                t = gp_graph::Tier{};
-                t.valid = true; t.gen = g_push_tuning_gen; t.L = L; t.rmax = rmax; t.coef_sum = csum; t.coef0 = coef[0];
-                rc = plan_tier(g, pl, (double)h[3] / (double)pilot, (long long)h[8], stream);
-                if (rc != GP_OK) return rc;
-                done = pilot;
-            }
-        }
-    }
-    const bool use_hash = want_hash && g->tier.valid && g->tier.enabled && g->tier.gen == g_push_tuning_gen &&
-                          g->tier.L == L && g->tier.rmax == rmax;
-    if (done < S && use_hash) {
-        const gp_graph::Tier &t = g->tier;
-        const long long rest = S - done;
-        if (g->d_redo_cap < (size_t)rest) {
+    if (cp.G > 0) {
+        rc = ensure_packed(g, stream);
+        if (rc != GP_OK) return rc;
+        if (g->cscratch_bytes < cp.bytes) {
             GP_CUDA_TRY(cudaStreamSynchronize(stream));
-            cudaFree(g->d_redo); g->d_redo = nullptr; g->d_redo_cap = 0;
-            GP_CUDA_TRY(cudaMalloc(&g->d_redo, sizeof(int) * (size_t)rest));
-            g->d_redo_cap = (size_t)rest;
+            if (g->ev_recorded) GP_CUDA_TRY(cudaEventSynchronize(g->ev_done));
+            cudaFree(g->cscratch); g->cscratch = nullptr; g->cscratch_bytes = 0;
+            GP_CUDA_TRY(cudaMalloc(&g->cscratch, cp.bytes));
+            g->cscratch_bytes = cp.bytes;
         }
-        char *hb = (char *)g->hscratch;
-        HashParams H{};
-        H.indptr = g->d_indptr; H.indices = g->d_indices; H.n = (int)g->n;
-        H.node_idx = d_node_idx + done; H.S = rest; H.coef = g->d_coef; H.L = L; H.rmax = rmax; H.K = K;
-        H.out_row = d_row + done * K; H.out_col = d_col + done * K; H.out_val = d_val + done * K;
-        H.out_val32 = d_val32 ? d_val32 + done * K : nullptr;
-        H.keys = (int *)(hb + t.off_keys); H.nxt = (double *)(hb + t.off_nxt); H.rsv = (double *)(hb + t.off_rsv);
-        H.push_start = (int *)(hb + t.off_ps); H.push_deg = (int *)(hb + t.off_pd); H.push_val = (double *)(hb + t.off_pv);
-        H.nxt_id = (int *)(hb + t.off_nid); H.tmp_key = (int *)(hb + t.off_tk); H.tmp_val = (double *)(hb + t.off_tv);
-        H.Cmax = t.Cmax; H.capP = t.capP; H.capL = t.capL;
-        H.load_pct = g_push_load_pct; H.list_div = std::max(g_push_list_div, 1);
-        H.redo = g->d_redo; H.redo_count = g->d_ctrl + 6;
-        H.queue = g->d_ctrl + 5; H.stats = g->d_ctrl + 1; H.cum = g->d_ctrl + 16; H.phase = g->d_ctrl + 24;
-        rc = launch_hash(H, t.block, t.G, (int)std::min<long long>(t.clusters, rest), stream);
+        if (g->d_redo_cap < (size_t)S) {
+            GP_CUDA_TRY(cudaStreamSynchronize(stream));
+            if (g->ev_recorded) GP_CUDA_TRY(cudaEventSynchronize(g->ev_done));
+            cudaFree(g->d_redo); g->d_redo = nullptr; g->d_redo_cap = 0;
+            GP_CUDA_TRY(cudaMalloc(&g->d_redo, sizeof(int) * (size_t)S));
+            g->d_redo_cap = (size_t)S;
+        }
+        char *cb = (char *)g->cscratch;
+        ClusterPushParams C{};
+        C.node_rec = g->d_node_rec; C.packed = g->d_packed; C.n = (int)g->n; C.idbits = g->idbits;
+        C.node_idx = d_node_idx; C.S = S; C.coef = g->d_coef; C.L = L; C.rmax = rmax; C.K = K;
+        C.out_row = d_row; C.out_col = d_col; C.out_val = d_val; C.out_val32 = d_val32;
+        C.push_start = (int *)(cb + cp.off_ps); C.push_len = (int *)(cb + cp.off_pl); C.push_add = (double *)(cb + cp.off_pa);
+        C.capP = cp.capP;
+        C.x_id = (int *)(cb + cp.off_xi); C.x_val = (double *)(cb + cp.off_xv); C.capX = cp.capX;
+        C.cand_id = (int *)(cb + cp.off_ci); C.cand_val = (double *)(cb + cp.off_cv);
+        C.hub_start = (int *)(cb + cp.off_hs); C.hub_deg = (int *)(cb + cp.off_hd); C.hub_add = (double *)(cb + cp.off_ha);
+        C.capHub = cp.capHub; C.hub_min_deg = cp.hub_min_deg;
+        C.max_probe = std::max(g_push_cluster_probe, 1);
+        C.queue = g->d_ctrl; C.stats = g->d_ctrl + 1; C.cum = g->d_ctrl + 16; C.phase = g->d_ctrl + 24;
+        C.redo = g->d_redo; C.redo_count = g->d_ctrl + 6;
+        rc = gpc_launch(C, cp.G, cp.clusters, stream);
         if (rc != GP_OK) return rc;
         launches++;
-        // second pass: whatever did not fit the tables, on the slabs (exits at once when the list is empty)
-        PushParams R = P;
-        R.node_idx = H.node_idx; R.S = rest;
-        R.out_row = H.out_row; R.out_col = H.out_col; R.out_val = H.out_val; R.out_val32 = H.out_val32;
-        R.epoch_base = (int)(g->epoch_base + done);
-        R.queue = g->d_ctrl + 7; R.redo = g->d_redo; R.redo_count = g->d_ctrl + 6;
-        rc = launch_slab(R, pl, stream);
-        if (rc != GP_OK) return rc;
-        launches++;
-    } else if (done < S) {
-        PushParams Q = P;
-        Q.node_idx = d_node_idx + done; Q.S = S - done;
-        Q.out_row = d_row + done * K; Q.out_col = d_col + done * K; Q.out_val = d_val + done * K;
-        Q.out_val32 = d_val32 ? d_val32 + done * K : nullptr;
-        Q.epoch_base = (int)(g->epoch_base + done);
-        Q.queue = g->d_ctrl + 7;
-        rc = launch_slab(Q, pl, stream);
-        if (rc != GP_OK) return rc;
-        launches++;
+        // second pass: what outgrew the tables or the streams, on the slabs (exits at once when the list is empty)
+        P.redo = g->d_redo; P.redo_count = g->d_ctrl + 6;
     }
+    rc = launch_slab(P, pl, stream);
+    if (rc != GP_OK) return rc;
+    launches++;
+    GP_CUDA_TRY(cudaEventRecord(g->ev_done, stream));
+    g->ev_recorded = true;
     g->epoch_base += S;
-    g->last.sources = S; g->last.ctas = std::min<long long>(pl.ctas, S); g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->hscratch_bytes);
-    g->last.scratch_mode = pl.mode; g->last.kernel_launches = launches;
+    g->last.sources = S;
+    g->last.ctas = cp.G > 0 ? (long long)cp.clusters * cp.G : std::min<long long>(pl.ctas, S);
+    g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->cscratch_bytes);
+    g->last.scratch_mode = pl.mode; g->last.kernel_launches = launches; g->last.cluster_size = cp.G;
     return GP_OK;
 }
 
@@ -1250,8 +1128,18 @@ int collect_stats(gp_graph *g, cudaStream_t stream) {
     g->last.edges_pushed = (int64_t)h[1];
     g->last.frontier_total = (int64_t)h[2];
     g->last.support_total = (int64_t)h[3];
+    if (h[4]) {
+        // the error word is sticky across calls until it is read here
+        GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl + 4, 0, sizeof(unsigned long long), stream));
+        GP_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    if (h[4] & kErrOverflow) {
+        // a truncated list leaves residues behind on the slabs: have the next call re-initialise them
+        g->scratch_mode = -1;
+        gp_set_error("frontier/support list outgrew its bound (rmax too small for the budget?)");
+        return GP_ERR_OVERFLOW;
+    }
     if (h[4] & kErrBadSource) { gp_set_error("node_idx contains an id outside [0, %lld)", g->n); return GP_ERR_INVALID; }
-    if (h[4] & kErrOverflow) { gp_set_error("frontier/support list outgrew its bound (rmax too small for the budget?)"); return GP_ERR_OVERFLOW; }
     return GP_OK;
 }
 
@@ -1261,6 +1149,7 @@ int graph_finish_create(gp_graph *g) {
     g->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : GP_NUM_SMS_FALLBACK;
     g->smem_optin = prop.sharedMemPerBlockOptin;
     GP_CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    GP_CUDA_TRY(cudaEventCreateWithFlags(&g->ev_done, cudaEventDisableTiming));
     GP_CUDA_TRY(cudaMalloc(&g->d_coef, sizeof(double) * kMaxLevels));
     GP_CUDA_TRY(cudaMalloc(&g->d_ctrl, sizeof(unsigned long long) * 32));
     // validate the CSR once, on the device (the reference validates nothing)
@@ -1335,9 +1224,11 @@ int gp_graph_create_device(const int32_t *d_indptr, int64_t n_nodes, const int32
 void gp_graph_destroy(gp_graph *g) {
     if (!g) return;
     DeviceGuard guard(g->device);
+    if (g->ev_recorded) cudaEventSynchronize(g->ev_done);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->owns_csr) { cudaFree(g->d_indptr); cudaFree(g->d_indices); }
-    cudaFree(g->d_node_rec); cudaFree(g->scratch); cudaFree(g->hscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
+    cudaFree(g->d_node_rec); cudaFree(g->d_packed); cudaFree(g->scratch); cudaFree(g->cscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
+    if (g->ev_done) cudaEventDestroy(g->ev_done);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }
@@ -1410,7 +1301,7 @@ int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset) {
     *out = g->last;
     out->edges_pushed = (int64_t)h[0]; out->frontier_total = (int64_t)h[1];
     out->support_total = (int64_t)h[2]; out->sources = (int64_t)h[3];
-    out->hash_sources = (int64_t)h[4]; out->hash_fallbacks = (int64_t)h[5];
+    out->cluster_sources = (int64_t)h[4]; out->redo_sources = (int64_t)h[5];
     return GP_OK;
 }
 
@@ -1429,8 +1320,8 @@ int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out) {
     std::lock_guard<std::mutex> lk(g->mu);
     DeviceGuard guard(g->device);
     if (g->last.sources > 0 && g->last.kernel_launches > 0) {
-        // the device-pointer entry point is asynchronous: wait for whatever stream it ran on
-        GP_CUDA_TRY(cudaDeviceSynchronize());
+        // the device-pointer entry point is asynchronous: wait for the push, whatever stream it ran on
+        if (g->ev_recorded) GP_CUDA_TRY(cudaEventSynchronize(g->ev_done));
         int rc = collect_stats(g, g->stream);
         if (rc != GP_OK) { *out = g->last; return rc; }
     }

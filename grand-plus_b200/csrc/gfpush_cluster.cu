@@ -1,0 +1,613 @@
+// gfpush_cluster.cu -- GFPush + top-k with ONE SOURCE PER THREAD-BLOCK CLUSTER (sm_100a).
+// Same computation as gfpush.cu (Graph::gfpush_omp, /root/reference/precompute/graph.h:53-131); this kernel is the
+// path for supports that outgrow one SM's shared memory (Reddit-, MAG-, Amazon2M-shape graphs):
+//
+//   * a cluster of G CTAs (1, 2, 4, 8 or 16) owns a source.  Node v belongs to CTA  hash(v) >> (32 - log2 G);  every
+//     CTA keeps an open-addressed {key, residue} table of 16 384 slots in its shared memory, PERSISTENT for the source,
+//     so the cluster offers G x 16 384 slots and the residues never leave the chip;
+//   * the reserve of a slot lives in a REGISTER of the thread that owns the slot (32 slots per thread, 512 threads):
+//     "reserve += coef * r" (graph.h:90) is one FMA, nothing is logged, merged or read-modify-written in memory, and
+//     the top-k selects straight out of the register file;
+//   * a level is   settle  ->  expand  ->  exchange:
+//       settle   every thread scans its 32 slots: a non-zero residue is credited to the reserve and zeroed; whether the
+//                node pushes (r >= rmax * deg, graph.h:94) is decided from a DEGREE CODE packed into the spare high
+//                bits of every CSR entry (and therefore of every table key): the {start, degree} record of a node is
+//                only fetched for the ~2 % of nodes that can pass -- no list of touched nodes, no first-touch
+//                detection, no per-node global access;
+//       expand   edge-balanced over the CTA's push list (block scan of the degrees + owner search, coalesced reads of
+//                the packed CSR); with G == 1 every edge is find-or-claim + fp64 add in the local table, with G > 1
+//                every edge (node, r/deg) is APPENDED to the stream of the CTA that owns the node (one shared-memory
+//                counter per destination, one atomic per warp and destination via match.any);
+//       exchange after a cluster barrier every CTA reads the G streams addressed to it (L2-resident, coalesced) and
+//                accumulates them into its table.  Entries of degree >= hub_min_deg are put on a cluster-wide list and
+//                every CTA expands a 1/G slice, so a 240 K-degree hub does not serialise on its owner;
+//   * top-k: every CTA radix-selects its own K largest reserves (gfpush.cu's MSD select, reading registers), writes
+//     them to a candidate buffer, and the cluster's first CTA selects the K largest of the G x K candidates;
+//   * a source whose table or stream overflows is handed to gfpush.cu's slab kernel through a redo list.
+#include "gfpush_cluster.h"
+#include "gfpush_shared.cuh"
+
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+namespace cg = cooperative_groups;
+
+namespace gpp {
+namespace {
+
+constexpr int CB = kClusterBlock;
+constexpr int SPT = kClusterSlots / CB;       // table slots (and reserve registers) per thread
+constexpr int kBuckets = kClusterSlots / 4;   // 4-key buckets: one 16-byte shared-memory read per probe
+constexpr int kEmpty = -1;
+constexpr int kEdgeUnroll = 4;
+
+struct CSmem {
+    unsigned off[CB + 1];      // exclusive scan of the tile's degrees, off[CB] = total
+    int start[CB];
+    double add[CB];
+    unsigned warp_scan[CB / 32 + 1];
+    unsigned hist[kHistBins];
+    unsigned long long bkey[kBucketCap];
+    int bid[kBucketCap];
+    unsigned cnt[kClusterMaxG];      // entries this CTA appended to the stream of each destination (this level)
+    unsigned pre[kClusterMaxG + 1];  // exchange / final select: prefix sums over the senders
+    long long it;                    // (first CTA) the cluster's current source
+    int n_push;                      // local push-list entries of this level
+    int n_out, n_bucket, n_cand;
+    int sel_bin, sel_above, sel_inbin;
+    // cluster-wide state, valid in the first CTA's copy
+    unsigned c_push[2];              // push-list entries of all CTAs, by level parity
+    unsigned c_hub[2];               // hub entries, by level parity
+    unsigned c_flags;                // 1 = hand the source to the slab kernel
+    long long ph[8], t_prev;
+};
+
+__device__ __forceinline__ unsigned hash_node(unsigned id) { return id * 2654435761u; }
+
+template <int G>
+struct Log2 { static constexpr int v = 1 + Log2<G / 2>::v; };
+template <>
+struct Log2<1> { static constexpr int v = 0; };
+
+// Slot of packed node `vp` in the table (claiming one when it is new), or -1 when `max_probe` buckets hold neither it
+// nor an empty slot.  Keys are never removed while a source is live and empties are taken in index order, so an
+// observed key is final and a node can never end up in two slots.
+__device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int max_probe) {
+    unsigned b = bucket;
+    for (int probe = 0; probe < max_probe; probe++, b = (b + 1) & (kBuckets - 1)) {
+        const int4 k4 = *reinterpret_cast<const int4 *>(keys + 4 * b);
+        const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int k = kk[i];
+            if (k == kEmpty) {
+                k = atomicCAS(keys + 4 * b + i, kEmpty, vp);
+                if (k == kEmpty) return (int)(4 * b + i);
+            }
+            if (k == vp) return (int)(4 * b + i);
+        }
+    }
+    return -1;
+}
+
+// The K largest of the items `each` enumerates (each(f) calls f(value > 0, id) for the calling thread's items; it is
+// invoked once per radix pass).  emit_fn(position, id, value) receives them in arbitrary order; returns their number.
+// MSD radix select on the fp64 bit pattern as in gfpush.cu.  Every thread of the CTA must call it.
+template <class Each, class Emit>
+__device__ __forceinline__ int block_topk(CSmem &sm, const int K, Each each, Emit emit_fn) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kHistBins; i += CB) sm.hist[i] = 0;
+    if (tid == 0) { sm.n_out = 0; sm.n_bucket = 0; }
+    __syncthreads();
+    each([&](double x, int) { atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u); });
+    __syncthreads();
+    int shift = 52, bits = 11;
+    unsigned long long prefix = 0;   // value of key >> (shift + bits) shared by the boundary bucket
+    int kk = K;
+    bool first = true;
+    unsigned long long Tkey = 0;
+    int want_bucket = 0;
+    for (;;) {
+        const unsigned total = select_bin_generic<CB>(sm.hist, sm.warp_scan, 1 << bits, kk, first, &sm.sel_bin,
+                                                      &sm.sel_above, &sm.sel_inbin);
+        if (first) kk = min(kk, (int)total);   // k = min(K, #positive): graph.h:113 + the v > 0 filter of :121
+        if (kk == 0) { want_bucket = 0; Tkey = ~0ull; break; }
+        const int bin = sm.sel_bin, above = sm.sel_above, inbin = sm.sel_inbin;
+        Tkey = (prefix << bits) | (unsigned long long)bin;
+        want_bucket = kk - above;
+        if (inbin <= kBucketCap || shift == 0) break;
+        kk = want_bucket; first = false; prefix = Tkey;
+        __syncthreads();
+        for (int i = tid; i < kHistBins; i += CB) sm.hist[i] = 0;
+        __syncthreads();
+        const int nshift = shift >= 11 ? shift - 11 : 0;
+        const int nbits = shift >= 11 ? 11 : shift;
+        each([&](double x, int) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+            if ((key >> shift) == prefix) atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
+        });
+        shift = nshift; bits = nbits;
+        __syncthreads();
+    }
+    each([&](double x, int id) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+        const unsigned long long t = key >> shift;
+        if (t > Tkey) {
+            emit_fn(atomicAdd(&sm.n_out, 1), id, x);
+        } else if (t == Tkey) {
+            const int pos = atomicAdd(&sm.n_bucket, 1);
+            if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = id; }
+        }
+    });
+    __syncthreads();
+    {
+        // rank-count the boundary bucket: keep its `want_bucket` largest (ties: lower position first)
+        const int nb = min(sm.n_bucket, kBucketCap);
+        for (int i = tid; i < nb; i += CB) {
+            const unsigned long long ki = sm.bkey[i];
+            int rank = 0;
+            for (int q = 0; q < nb; q++) {
+                const unsigned long long kq = sm.bkey[q];
+                rank += (kq > ki) || (kq == ki && q < i);
+            }
+            if (rank < want_bucket) emit_fn(atomicAdd(&sm.n_out, 1), sm.bid[i], __longlong_as_double((long long)ki));
+        }
+    }
+    __syncthreads();
+    return sm.n_out;
+}
+
+template <int G>
+__global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPushParams P) {
+    constexpr int LOGG = Log2<G>::v;
+    constexpr int kOwnerShift = G > 1 ? 32 - LOGG : 31;   // hash >> kOwnerShift = owning CTA (unused when G == 1)
+    __shared__ CSmem sm;
+    extern __shared__ double s_vals[];                      // [kClusterSlots] next-level residues
+    int *s_keys = reinterpret_cast<int *>(s_vals + kClusterSlots);   // [kClusterSlots] packed node, kEmpty = free
+
+    const int tid = threadIdx.x;
+    const int lane = gp_lane();
+    unsigned rank = 0;
+    if (G > 1) rank = cg::this_cluster().block_rank();
+    const long long cta = blockIdx.x;
+    const long long cta0 = cta - rank;          // the cluster's first CTA
+    const long long cid = cta / G;
+    CSmem *ldr = &sm;                            // the first CTA's shared state
+    if (G > 1) ldr = cg::this_cluster().map_shared_rank(&sm, 0);
+    auto csync = [&]() { if (G > 1) cg::this_cluster().sync(); else __syncthreads(); };
+
+    const unsigned idmask = P.idbits >= 32 ? 0xFFFFFFFFu : ((1u << P.idbits) - 1u);
+    const bool has_code = P.idbits < 32;
+    int *push_start = P.push_start + cta * P.capP;
+    int *push_len = P.push_len + cta * P.capP;
+    double *push_add = P.push_add + cta * P.capP;
+    int *hub_start = P.hub_start + cid * P.capHub;
+    int *hub_deg = P.hub_deg + cid * P.capHub;
+    double *hub_add = P.hub_add + cid * P.capHub;
+    int *x_id = P.x_id + cta * G * P.capX;       // my streams, one per destination
+    double *x_val = P.x_val + cta * G * P.capX;
+    unsigned long long *err = P.stats + 3;
+
+    for (int i = tid; i < kClusterSlots; i += CB) { s_vals[i] = 0.0; s_keys[i] = kEmpty; }
+    double rsv[SPT];                             // reserve of slot j * CB + tid
+#pragma unroll
+    for (int j = 0; j < SPT; j++) rsv[j] = 0.0;
+    if (tid == 0) {
+        sm.c_push[0] = sm.c_push[1] = 0; sm.c_hub[0] = sm.c_hub[1] = 0; sm.c_flags = 0; sm.n_push = 0;
+        for (int i = 0; i < 8; i++) sm.ph[i] = 0;
+    }
+    if (tid < kClusterMaxG) sm.cnt[tid] = 0;
+    unsigned long long st_edges = 0, st_sources = 0, st_cluster = 0, st_redo = 0;   // thread 0 only
+    unsigned st_frontier = 0, st_support = 0;                                         // every thread, reduced at the end
+    const long long t_begin = clock64();
+    if (tid == 0) sm.t_prev = t_begin;
+#define GPC_PHASE(i) do { if (tid == 0) { const long long t_now = clock64(); sm.ph[i] += t_now - sm.t_prev; sm.t_prev = t_now; } } while (0)
+
+    for (;;) {
+        if (rank == 0 && tid == 0) sm.it = (long long)atomicAdd(P.queue, 1ull);
+        csync();
+        const long long it = ldr->it;
+        if (it >= P.S) break;
+        const int src = P.node_idx[it];
+        if (src < 0 || src >= P.n) {   // refuse instead of reading out of bounds
+            if (rank == 0) {
+                if (tid == 0) atomicOr(err, kErrBadSource);
+                for (int i = tid; i < P.K; i += CB) {
+                    const long long o = it * P.K + i;
+                    P.out_row[o] = 0; P.out_col[o] = 0; P.out_val[o] = 0.0;
+                    if (P.out_val32) P.out_val32[o] = 0.f;
+                }
+            }
+            csync();   // the next fetch must not overwrite sm.it before everyone has read it
+            continue;
+        }
+        const int2 src_rec = __ldg(P.node_rec + src);
+        unsigned src_front = 0;                 // work counters of this source (dropped when it is handed over)
+        unsigned long long src_edges = 0;
+        int src_packed = src;
+        if (has_code) {
+            const unsigned cap = (1u << (32 - P.idbits)) - 2u;
+            src_packed = (int)((unsigned)src | (min((unsigned)src_rec.y, cap) << P.idbits));
+        }
+        // level 0: residue = {src: 1} (graph.h:80); the source's owner seeds its (empty) table
+        if (tid == 0) {
+            if (rank == 0) { st_sources++; st_cluster++; }
+            const unsigned h = hash_node((unsigned)src);
+            const unsigned owner = G > 1 ? h >> kOwnerShift : 0u;
+            if (owner == rank) {
+                const int slot = find_slot(s_keys, (h >> (32 - LOGG - 12)) & (kBuckets - 1), src_packed, 1);
+                s_vals[slot] = 1.0;
+            }
+        }
+        __syncthreads();
+        GPC_PHASE(0);
+
+        for (int level = 0; level < P.L; level++) {   // graph.h:83 (+ the last level, :104-110)
+            const int par = level & 1;
+            const bool will_push = level < P.L - 1;
+            const double c = P.coef[level];
+            // ---------------------------------------------------------------- settle (graph.h:85-93,102)
+            bool ovf = false;
+#pragma unroll
+            for (int j = 0; j < SPT; j++) {
+                const int slot = j * CB + tid;
+                const double r = s_vals[slot];
+                if (r != 0.0) {
+                    s_vals[slot] = 0.0;
+                    rsv[j] += c * r;                                   // graph.h:90 / :106
+                    src_front++;
+                    if (will_push) {
+                        const unsigned key = (unsigned)s_keys[slot];
+                        const unsigned code = has_code ? key >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
+                        if (r >= P.rmax * (double)code) {              // necessary for graph.h:94; exact test below
+                            const int2 rec = __ldg(P.node_rec + (key & idmask));
+                            const unsigned d = (unsigned)rec.y;
+                            int e_start = -1; unsigned e_len = 0; double e_add = r;
+                            if (d == 0) { e_len = 1; }                                             // graph.h:91-93: back to the source
+                            else if (r >= P.rmax * (double)d) { e_start = rec.x; e_len = d; e_add = r / (double)d; }   // graph.h:94-95
+                            if (e_len) {
+                                if (G > 1 && e_len >= (unsigned)P.hub_min_deg) {
+                                    const unsigned p = atomicAdd(&ldr->c_hub[par], 1u);
+                                    if (p < (unsigned)P.capHub) { hub_start[p] = e_start; hub_deg[p] = (int)e_len; hub_add[p] = e_add; }
+                                    else ovf = true;
+                                } else {
+                                    const int p = atomicAdd(&sm.n_push, 1);
+                                    if (p < P.capP) { push_start[p] = e_start; push_len[p] = (int)e_len; push_add[p] = e_add; }
+                                    else ovf = true;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (ovf) atomicOr(&ldr->c_flags, 1u);
+            __syncthreads();
+            GPC_PHASE(2);
+            if (!will_push) break;
+            if (G > 1) {
+                if (tid == 0 && sm.n_push) atomicAdd(&ldr->c_push[par], (unsigned)sm.n_push);
+                csync();   // #1: every CTA's push list and the hub list of this level are complete
+            }
+            const int n_local = min((long long)sm.n_push, P.capP);
+            const int n_hub = G > 1 ? (int)min(ldr->c_hub[par], (unsigned)P.capHub) : 0;
+            const unsigned n_all = G > 1 ? ldr->c_push[par] + ldr->c_hub[par] : (unsigned)n_local;
+            if (n_all == 0) break;   // nothing pushes: every later residue is zero (the reserve is complete)
+            if (G > 1) {
+                if (rank == 0 && tid == 0) { sm.c_push[par ^ 1] = 0; sm.c_hub[par ^ 1] = 0; }
+                if (tid < G) sm.cnt[tid] = 0;   // the receivers finished reading them before barrier #1
+            }
+            // ---------------------------------------------------------------- expand (graph.h:94-100)
+            ovf = false;
+            const int n_items = n_local + n_hub;
+            for (int base = 0; base < n_items; base += CB) {
+                const int j = base + tid;
+                unsigned len = 0;
+                int start = 0;
+                double add = 0.0;
+                if (j < n_local) { start = push_start[j]; len = (unsigned)push_len[j]; add = push_add[j]; }
+                else if (j < n_items) {   // this CTA's slice of a hub entry
+                    const int h = j - n_local;
+                    const unsigned d = (unsigned)__ldcg(hub_deg + h);
+                    const unsigned lo = (unsigned)((unsigned long long)d * rank / G), hi = (unsigned)((unsigned long long)d * (rank + 1) / G);
+                    start = __ldcg(hub_start + h) + (int)lo; len = hi - lo; add = __ldcg(hub_add + h);
+                }
+                unsigned total;
+                const unsigned excl = gp_block_exclusive_scan<CB>(len, sm.warp_scan, total);
+                sm.off[tid] = excl; sm.start[tid] = start; sm.add[tid] = add;
+                if (tid == 0) { sm.off[CB] = total; src_edges += total; }
+                __syncthreads();
+                for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += CB * kEdgeUnroll) {
+                    int vp[kEdgeUnroll];
+                    double av[kEdgeUnroll];
+                    bool ok[kEdgeUnroll];
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        const unsigned e = e0 + q * CB + lane;
+                        ok[q] = e < total;
+                        vp[q] = src_packed; av[q] = 0.0;
+                        if (ok[q]) {
+                            const int t = owner_of_edge<CB>(sm.off, e);
+                            const int st = sm.start[t];
+                            av[q] = sm.add[t];
+                            if (st >= 0) vp[q] = __ldcs(P.packed + st + (e - sm.off[t]));   // graph.h:96-97
+                        }
+                    }
+                    if (G == 1) {
+                        int slot[kEdgeUnroll];
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            slot[q] = 0;
+                            if (ok[q]) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> 20) & (kBuckets - 1), vp[q], P.max_probe);
+                        }
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            if (ok[q]) {
+                                if (slot[q] >= 0) atomicAdd(s_vals + slot[q], av[q]);   // graph.h:98
+                                else ovf = true;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            const unsigned act = __ballot_sync(0xffffffffu, ok[q]);
+                            if (ok[q]) {
+                                const unsigned dst = hash_node((unsigned)vp[q] & idmask) >> kOwnerShift;
+                                const unsigned peers = __match_any_sync(act, dst);
+                                const int leader = __ffs(peers) - 1;
+                                unsigned pos = 0;
+                                if (lane == leader) pos = atomicAdd(&sm.cnt[dst], (unsigned)__popc(peers));
+                                pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                                if (pos < (unsigned)P.capX) {
+                                    x_id[dst * P.capX + pos] = vp[q];
+                                    x_val[dst * P.capX + pos] = av[q];
+                                } else ovf = true;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (ovf) atomicOr(&ldr->c_flags, 1u);
+            if (tid == 0) sm.n_push = 0;
+            GPC_PHASE(1);
+            if (G > 1) {
+                csync();   // #2: every stream of this level is complete and visible
+                // ------------------------------------------------------------ exchange: accumulate what was sent to me
+                if (tid < G) sm.pre[tid + 1] = min(cg::this_cluster().map_shared_rank(&sm, tid)->cnt[rank], (unsigned)P.capX);
+                __syncthreads();
+                if (tid == 0) {
+                    sm.pre[0] = 0;
+                    for (int s = 0; s < G; s++) sm.pre[s + 1] += sm.pre[s];
+                }
+                __syncthreads();
+                const unsigned total = sm.pre[G];
+                ovf = false;
+                for (unsigned e0 = tid; e0 < total; e0 += CB * kEdgeUnroll) {
+                    int vp[kEdgeUnroll];
+                    double av[kEdgeUnroll];
+                    bool ok[kEdgeUnroll];
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        const unsigned e = e0 + q * CB;
+                        ok[q] = e < total;
+                        vp[q] = 0; av[q] = 0.0;
+                        if (ok[q]) {
+                            int s = 0;
+#pragma unroll
+                            for (int k = 1; k < G; k++) s += e >= sm.pre[k];
+                            const long long a = ((cta0 + s) * G + rank) * P.capX + (e - sm.pre[s]);
+                            vp[q] = __ldcg(P.x_id + a);
+                            av[q] = __ldcg(P.x_val + a);
+                        }
+                    }
+                    int slot[kEdgeUnroll];
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        slot[q] = 0;
+                        if (ok[q]) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> (32 - LOGG - 12)) & (kBuckets - 1), vp[q], P.max_probe);
+                    }
+#pragma unroll
+                    for (int q = 0; q < kEdgeUnroll; q++) {
+                        if (ok[q]) {
+                            if (slot[q] >= 0) atomicAdd(s_vals + slot[q], av[q]);   // graph.h:98
+                            else ovf = true;
+                        }
+                    }
+                }
+                if (ovf) atomicOr(&ldr->c_flags, 1u);
+                GPC_PHASE(3);
+            }
+            __syncthreads();
+        }
+        // ------------------------------------------------------------------ top-k, graph.h:111-126
+        csync();   // #C: every CTA's overflow flag has landed
+        const bool redo = ldr->c_flags != 0;
+        if (!redo) { st_frontier += src_front; st_edges += src_edges; }
+        auto each_reg = [&](auto f) {
+#pragma unroll
+            for (int j = 0; j < SPT; j++)
+                if (rsv[j] > 0.0) f(rsv[j], (int)((unsigned)s_keys[j * CB + tid] & idmask));
+        };
+        if (!redo) {
+            if (G == 1) {
+                const int n = block_topk(sm, P.K, each_reg, [&](int pos, int id, double v) {
+                    const long long o = it * P.K + pos;
+                    P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
+                    if (P.out_val32) P.out_val32[o] = (float)v;
+                });
+                // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
+                for (int i = n + tid; i < P.K; i += CB) {
+                    const long long o = it * P.K + i;
+                    P.out_row[o] = 0; P.out_col[o] = 0; P.out_val[o] = 0.0;
+                    if (P.out_val32) P.out_val32[o] = 0.f;
+                }
+            } else {
+                int *cand_id = P.cand_id + cta * P.K;
+                double *cand_val = P.cand_val + cta * P.K;
+                const int n = block_topk(sm, P.K, each_reg, [&](int pos, int id, double v) { cand_id[pos] = id; cand_val[pos] = v; });
+                if (tid == 0) sm.n_cand = n;
+            }
+        }
+        // the table is empty again for the next source
+#pragma unroll
+        for (int j = 0; j < SPT; j++) {
+            const int slot = j * CB + tid;
+            if (s_keys[slot] != kEmpty) { st_support += redo ? 0u : 1u; s_keys[slot] = kEmpty; }
+            rsv[j] = 0.0;
+        }
+        if (G > 1) {
+            csync();   // #A: candidates of every CTA are visible
+            if (rank == 0) {
+                if (redo) {
+                    if (tid == 0) { P.redo[atomicAdd(P.redo_count, 1ull)] = (int)it; st_redo++; st_sources--; st_cluster--; }
+                } else {
+                    if (tid < G) sm.pre[tid + 1] = (unsigned)cg::this_cluster().map_shared_rank(&sm, tid)->n_cand;
+                    __syncthreads();
+                    if (tid == 0) {
+                        sm.pre[0] = 0;
+                        for (int s = 0; s < G; s++) sm.pre[s + 1] += sm.pre[s];
+                    }
+                    __syncthreads();
+                    const unsigned total = sm.pre[G];
+                    auto each_cand = [&](auto f) {
+                        for (unsigned e = tid; e < total; e += CB) {
+                            int s = 0;
+#pragma unroll
+                            for (int k = 1; k < G; k++) s += e >= sm.pre[k];
+                            const long long a = (cta0 + s) * P.K + (e - sm.pre[s]);
+                            f(__ldcg(P.cand_val + a), __ldcg(P.cand_id + a));
+                        }
+                    };
+                    const int n = block_topk(sm, P.K, each_cand, [&](int pos, int id, double v) {
+                        const long long o = it * P.K + pos;
+                        P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
+                        if (P.out_val32) P.out_val32[o] = (float)v;
+                    });
+                    for (int i = n + tid; i < P.K; i += CB) {
+                        const long long o = it * P.K + i;
+                        P.out_row[o] = 0; P.out_col[o] = 0; P.out_val[o] = 0.0;
+                        if (P.out_val32) P.out_val32[o] = 0.f;
+                    }
+                }
+                if (tid == 0) { sm.c_push[0] = sm.c_push[1] = 0; sm.c_hub[0] = sm.c_hub[1] = 0; sm.c_flags = 0; }
+            }
+        } else {
+            if (redo && tid == 0) { P.redo[atomicAdd(P.redo_count, 1ull)] = (int)it; st_redo++; st_sources--; st_cluster--; }
+            if (tid == 0) sm.c_flags = 0;
+        }
+        if (tid == 0) sm.n_push = 0;
+        if (tid < kClusterMaxG) sm.cnt[tid] = 0;
+        __syncthreads();
+        GPC_PHASE(4);
+    }
+    st_frontier = __reduce_add_sync(0xffffffffu, st_frontier);
+    st_support = __reduce_add_sync(0xffffffffu, st_support);
+    if (lane == 0) {
+        if (st_frontier) { atomicAdd(P.stats + 1, (unsigned long long)st_frontier); atomicAdd(P.cum + 1, (unsigned long long)st_frontier); }
+        if (st_support) { atomicAdd(P.stats + 2, (unsigned long long)st_support); atomicAdd(P.cum + 2, (unsigned long long)st_support); }
+    }
+    if (tid == 0) {
+        sm.ph[7] = clock64() - t_begin;
+        for (int i = 0; i < 8; i++) atomicAdd(P.phase + i, (unsigned long long)sm.ph[i]);
+        atomicAdd(P.stats + 0, st_edges);
+        atomicAdd(P.cum + 0, st_edges);
+        atomicAdd(P.cum + 3, st_sources);
+        atomicAdd(P.cum + 4, st_cluster);
+        atomicAdd(P.cum + 5, st_redo);
+    }
+    if (G > 1) cg::this_cluster().sync();   // nobody leaves while its shared memory may still be read
+}
+#undef GPC_PHASE
+
+__global__ void pack_indices_kernel(const int2 *node_rec, const int *indices, long long nnz, int idbits, int *packed) {
+    const unsigned cap = (1u << (32 - idbits)) - 2u;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
+        const unsigned v = (unsigned)indices[i];
+        const unsigned d = (unsigned)__ldg(&node_rec[v].y);
+        packed[i] = (int)(v | (min(d, cap) << idbits));
+    }
+}
+
+template <int G>
+int launch_config(int clusters, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_cluster_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)gpc_dynamic_smem()));
+        if (G > 8) GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_cluster_kernel<G>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured = true;
+    }
+    *cfg = cudaLaunchConfig_t{};
+    cfg->blockDim = dim3(CB);
+    cfg->gridDim = dim3((unsigned)(clusters * G));
+    cfg->dynamicSmemBytes = gpc_dynamic_smem();
+    cfg->stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)G; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg->attrs = attr;
+    cfg->numAttrs = G > 1 ? 1 : 0;
+    return GP_OK;
+}
+
+template <int G>
+int max_clusters_t(int num_sms, int *out) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    int rc = launch_config<G>(std::max(num_sms / G, 1), &cfg, attr, nullptr);
+    if (rc != GP_OK) return rc;
+    if (G == 1) { *out = num_sms; return GP_OK; }
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, gfpush_cluster_kernel<G>, &cfg);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    *out = n;
+    return GP_OK;
+}
+
+template <int G>
+int launch_t(const ClusterPushParams &P, int clusters, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg; cudaLaunchAttribute attr[1];
+    int rc = launch_config<G>(clusters, &cfg, attr, stream);
+    if (rc != GP_OK) return rc;
+    GP_CUDA_TRY(cudaLaunchKernelEx(&cfg, gfpush_cluster_kernel<G>, P));
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+}  // namespace
+
+size_t gpc_dynamic_smem() { return (size_t)kClusterSlots * 12; }
+
+int gpc_pack_indices(const int2 *node_rec, const int *indices, long long nnz, int idbits, int *packed, int num_sms,
+                     cudaStream_t stream) {
+    if (nnz == 0) return GP_OK;
+    pack_indices_kernel<<<num_sms * 8, 256, 0, stream>>>(node_rec, indices, nnz, idbits, packed);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+int gpc_max_clusters(int G, int num_sms, int *out) {
+    switch (G) {
+        case 1: return max_clusters_t<1>(num_sms, out);
+        case 2: return max_clusters_t<2>(num_sms, out);
+        case 4: return max_clusters_t<4>(num_sms, out);
+        case 8: return max_clusters_t<8>(num_sms, out);
+        case 16: return max_clusters_t<16>(num_sms, out);
+    }
+    gp_set_error("cluster size must be 1, 2, 4, 8 or 16 (got %d)", G);
+    return GP_ERR_INVALID;
+}
+
+int gpc_launch(const ClusterPushParams &P, int G, int clusters, cudaStream_t stream) {
+    switch (G) {
+        case 1: return launch_t<1>(P, clusters, stream);
+        case 2: return launch_t<2>(P, clusters, stream);
+        case 4: return launch_t<4>(P, clusters, stream);
+        case 8: return launch_t<8>(P, clusters, stream);
+        case 16: return launch_t<16>(P, clusters, stream);
+    }
+    gp_set_error("cluster size must be 1, 2, 4, 8 or 16 (got %d)", G);
+    return GP_ERR_INVALID;
+}
+
+}  // namespace gpp

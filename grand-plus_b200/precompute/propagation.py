@@ -115,9 +115,11 @@ class Graph:
                                        _ptr(row_idx), _ptr(col_idx), _ptr(value)))
 
     # -- device-resident variant (Pi stays on the GPU) ------------------
-    def gfpush_device(self, node_idx_t, coef, rmax, K, want_fp32=True, stream=None):
+    def gfpush_device(self, node_idx_t, coef, rmax, K, want_fp32=True, stream=None, check=False):
         """node_idx_t: int32 CUDA tensor [S].  Returns (row, col, val64, val32|None) CUDA tensors
-        [S, K].  Asynchronous on the current torch stream."""
+        [S, K].  Asynchronous on the current torch stream.  Device-side refusals (a source id outside
+        the graph, a list that outgrew its bound) are sticky on the handle and raise at the next
+        ``check_errors()`` / ``last_stats()``; ``check=True`` waits for the push and raises at once."""
         import torch
         if node_idx_t.dtype != torch.int32 or not node_idx_t.is_cuda:
             raise ValueError("node_idx_t must be an int32 CUDA tensor")
@@ -134,7 +136,14 @@ class Graph:
             self._h, ctypes.c_void_p(node_idx_t.data_ptr()), S, _ptr(coef), int(coef.shape[0]), float(rmax), K,
             ctypes.c_void_p(row.data_ptr()), ctypes.c_void_p(col.data_ptr()), ctypes.c_void_p(val.data_ptr()),
             ctypes.c_void_p(val32.data_ptr() if val32 is not None else 0), ctypes.c_void_p(st)))
+        if check:
+            self.check_errors()
         return row, col, val, val32
+
+    def check_errors(self) -> None:
+        """Waits for the handle's last push and raises GPError if the device refused anything since
+        the last check (gp_gfpush_device itself returns before the kernels run)."""
+        self.last_stats()
 
     def last_stats(self) -> dict:
         st = _lib.PushStats()
@@ -143,10 +152,12 @@ class Graph:
 
 
     def phase_cycles(self, reset=False) -> dict:
-        """SM cycles per phase of the hash tier's leader CTAs (profiling hook)."""
+        """SM cycles per phase, summed over the persistent CTAs (profiling hook).  The cluster kernel reports
+        fetch / expand / settle / exchange / topk / resident, the per-CTA kernels fetch / expand / settle / reserve merge /
+        topk / the widest level's expand and settle / resident."""
         out = (ctypes.c_uint64 * 8)()
         _lib.check(self._lib.gp_gfpush_phase_cycles(self._h, ctypes.byref(out), int(bool(reset))))
-        names = ("fetch", "grow", "expand", "settle", "topk", "wide_expand", "wide_settle", "resident")
+        names = ("fetch", "expand", "settle", "merge_or_exchange", "topk", "wide_expand", "wide_settle", "resident")
         return dict(zip(names, [int(x) for x in out]))
 
     def cumulative_stats(self, reset=False) -> dict:

@@ -105,8 +105,10 @@ typedef struct {
     int64_t scratch_bytes;   /* device scratch held by the handle                     */
     int32_t scratch_mode;    /* mode actually used (gp_scratch_mode)                  */
     int32_t kernel_launches; /* kernels launched by the call                          */
-    int64_t hash_sources;    /* cumulative stats only: sources finished on the L2-resident hash tier  */
-    int64_t hash_fallbacks;  /* cumulative stats only: sources handed over to the direct-addressed slabs */
+    int64_t cluster_sources; /* cumulative stats only: sources finished by the cluster kernel          */
+    int64_t redo_sources;    /* cumulative stats only: sources it handed over to the slab kernel       */
+    int32_t cluster_size;    /* CTAs per source of the cluster kernel (0 = per-CTA kernels only)       */
+    int32_t reserved;
 } gp_push_stats;
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out);
 /* Counters summed over every gfpush since creation / the last reset (device-wide synchronise);

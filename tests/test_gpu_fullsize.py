@@ -1,6 +1,8 @@
-"""GPU tests at BASELINE.json's FULL sizes (configs[2], the Reddit-shape graph bench.py times): the oracle on a
-sample of rows, and size-independent properties on all of them -- agreement between the residue-table tiers,
-idempotence, mass bounds, the work bound (L-1)/rmax, linearity of the aggregation in X."""
+"""GPU tests at BASELINE.json's FULL sizes -- configs[2] (Reddit-shape, the graph bench.py times), configs[3]
+(Amazon2M-shape, rmax 1e-6, K 64: supports of 150 K nodes, a 241 K-degree hub) and configs[4] (MAG-Scholar-C-shape,
+10.5 M nodes, order 10): the oracle on a sample of rows (hub source included), the oracle's work counters, and
+size-independent properties on all rows -- agreement between the kernels (cluster kernel / shared-memory table in
+front of the slabs / plain slabs), idempotence, mass bounds, the work bound (L-1)/rmax, linearity of the aggregation."""
 import numpy as np
 import pytest
 
@@ -12,62 +14,100 @@ pytestmark = pytest.mark.gpu
 N, DRAWS, F = 232_965, 11_606_919, 602          # bench.WORKLOADS["reddit"]
 ORDER, ALPHA, RMAX, K = 6, 0.05, 1e-5, 32       # scripts/run_reddit.sh:7, K per BASELINE.json
 
+# name -> (nodes, edge draws, order, alpha, rmax, K, sources, expected cluster size, max degree at least)
+SHAPES = {
+    "reddit": (232_965, 11_606_919, 6, 0.05, 1e-5, 32, 4096, 2, 70_000),      # scripts/run_reddit.sh:7
+    "amazon2m": (2_449_029, 61_859_140, 6, 0.2, 1e-6, 64, 768, 16, 200_000),  # scripts/run_amazon2m.sh:7
+    "mag": (10_541_560, 265_219_994, 10, 0.2, 1e-5, 32, 2048, 2, 500_000),    # scripts/run_mag.sh:7
+}
+TIER_TUNING = {"cluster": dict(push_cluster=1), "table": dict(push_cluster=0, push_smem_hash=2),
+               "slabs": dict(push_cluster=0, push_smem_hash=0)}
+TUNING_DEFAULTS = dict(push_cluster=1, push_smem_hash=1)
 
-@pytest.fixture(scope="module")
-def reddit_shape():
+
+def _build(shape):
     import torch
     from grandplus_b200 import synth
     from grandplus_b200.precompute import propagation
-    indptr, indices = synth.powerlaw_csr(N, DRAWS, seed=0, device="cuda")
+    n, draws, order, alpha, rmax, k, S, G, dmin = SHAPES[shape]
+    indptr, indices = synth.powerlaw_csr(n, draws, seed=0, device="cuda")
     graph = propagation.Graph.from_device_csr(indptr, indices)
-    src = synth.sources(N, 4096, seed=7, device="cuda")
-    hub = (indptr[1:] - indptr[:-1]).argmax().to(torch.int32)
-    src[0] = hub                                  # a 75 K-degree source: level 0 is expanded by the whole CTA
+    src = synth.sources(n, S, seed=7, device="cuda")
+    deg = indptr[1:] - indptr[:-1]
+    assert int(deg.max()) >= dmin
+    src[0] = deg.argmax().to(torch.int32)         # the hub as a source: level 0 is expanded by the whole CTA / cluster
     return indptr, indices, graph, src.contiguous()
 
 
-def _rows(col, val):
-    return og.rows_as_sets(col.cpu().numpy().reshape(-1), val.cpu().numpy().reshape(-1), K)
+@pytest.fixture(scope="module")
+def reddit_shape():
+    return _build("reddit")
 
 
-def test_gfpush_full_size_tiers_agree_and_match_oracle(reddit_shape):
+def _rows(col, val, k=K):
+    return og.rows_as_sets(col.cpu().numpy().reshape(-1), val.cpu().numpy().reshape(-1), k)
+
+
+@pytest.mark.parametrize("shape", ["reddit", "amazon2m", "mag"])
+def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
     import torch
     from grandplus_b200 import _lib
-    indptr, indices, graph, src = reddit_shape
-    coef = og.coef_for("ppr", ORDER, ALPHA)
+    n, draws, order, alpha, rmax, k, S, G, _ = SHAPES[shape]
+    indptr, indices, graph, src = request.getfixturevalue("reddit_shape") if shape == "reddit" else _build(shape)
+    coef = og.coef_for("ppr", order, alpha)
+    tiers = ("cluster", "table", "slabs") if shape != "amazon2m" else ("cluster", "slabs")
     out = {}
     try:
-        for tier, mode in (("table", 2), ("slabs", 0)):
-            _lib.set_tuning("push_smem_hash", mode)
+        for tier in tiers:
+            for key, v in TIER_TUNING[tier].items():
+                _lib.set_tuning(key, v)
             graph.cumulative_stats(reset=True)
-            row, col, val, _ = graph.gfpush_device(src, coef, RMAX, K, want_fp32=True)
-            torch.cuda.synchronize()
-            out[tier] = (row, col, val, graph.cumulative_stats())
+            row, col, val, _ = graph.gfpush_device(src, coef, rmax, k, want_fp32=True, check=True)
+            out[tier] = (row, col, val, graph.cumulative_stats(), graph.last_stats())
     finally:
-        _lib.set_tuning("push_smem_hash", 1)
-    (_, ca, va, sa), (_, cb, vb, sb) = out["table"], out["slabs"]
-    # work counters are integers of the algorithm: both tiers count the same pushes, frontiers and supports
-    for k in ("edges_pushed", "frontier_total", "support_total", "sources"):
-        assert abs(sa[k] - sb[k]) <= 1e-6 * sb[k], (k, sa[k], sb[k])
+        for key, v in TUNING_DEFAULTS.items():
+            _lib.set_tuning(key, v)
+    # the cluster kernel took (nearly) every source, at the cluster size the shape calls for
+    sc, lc = out["cluster"][3], out["cluster"][4]
+    assert lc["cluster_size"] == G, lc
+    assert sc["cluster_sources"] + sc["redo_sources"] == len(src) and sc["redo_sources"] <= 0.05 * len(src), sc
+    _, cb, vb, sb, _ = out["slabs"]
     # the work bound of SURVEY 7: a level pushes at most 1/rmax edges (+ the source's own degree at level 0)
-    assert sa["edges_pushed"] <= len(src) * ((ORDER - 1) / RMAX + 80_000)
-    same = 0
-    for (ac, av), (bc, bv) in zip(_rows(ca, va), _rows(cb, vb)):
-        assert len(ac) == len(bc)
-        if np.array_equal(ac, bc):
-            same += 1
-            np.testing.assert_allclose(av, bv, rtol=1e-11, atol=0)
-        else:   # only a tie at the cut may differ
-            assert abs(av.min() - bv.min()) <= 1e-9 * bv.min()
-    assert same >= 0.85 * len(src)   # exact ties at the cut are common (symmetric neighbourhoods): ~8 % of rows
-    # mass: a row never sums above 1 (coef sums to 1, pushes only lose mass) and keeps at least coef[0] on the source
-    sums = va.reshape(-1, K).sum(1)
-    assert float(sums.max()) <= 1.0 + 1e-12 and float(sums.min()) >= coef[0] * (1 - 1e-12)
-    # the oracle itself on a sample of rows (hub source included)
+    assert sb["edges_pushed"] <= len(src) * ((order - 1) / rmax + 700_000)
+    rb = _rows(cb, vb, k)
+    for tier in tiers[:-1]:
+        _, ca, va, sa, _ = out[tier]
+        # work counters are integers of the algorithm: every kernel counts the same pushes, frontiers and supports
+        for key in ("edges_pushed", "frontier_total", "support_total", "sources"):
+            assert abs(sa[key] - sb[key]) <= 1e-6 * sb[key], (tier, key, sa[key], sb[key])
+        same = 0
+        for (ac, av), (bc, bv) in zip(_rows(ca, va, k), rb):
+            assert len(ac) == len(bc)
+            if np.array_equal(ac, bc):
+                same += 1
+                np.testing.assert_allclose(av, bv, rtol=1e-11, atol=0)
+            else:   # only a tie at the cut may differ
+                assert abs(av.min() - bv.min()) <= 1e-9 * bv.min()
+        assert same >= 0.85 * len(src)   # exact ties at the cut are common (symmetric neighbourhoods): ~8 % of rows
+        # mass: a row never sums above 1 (coef sums to 1, pushes only lose mass) and keeps at least coef[0] on the source
+        sums = va.reshape(-1, k).sum(1)
+        assert float(sums.max()) <= 1.0 + 1e-12 and float(sums.min()) >= coef[0] * (1 - 1e-12)
+    # the oracle itself on a sample of rows (hub source included), rows and work counters
     ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
-    worst = check_topk_rows(ip, ix, src.cpu().numpy(), coef, RMAX, K, ca.cpu().numpy().reshape(-1),
-                            va.cpu().numpy().reshape(-1), row=out["table"][0].cpu().numpy().reshape(-1), max_rows=12)
+    row, ca, va = out["cluster"][:3]
+    worst = check_topk_rows(ip, ix, src.cpu().numpy(), coef, rmax, k, ca.cpu().numpy().reshape(-1),
+                            va.cpu().numpy().reshape(-1), row=row.cpu().numpy().reshape(-1), max_rows=12)
     assert worst < 1e-11
+    sample = src[:24].contiguous()
+    graph.cumulative_stats(reset=True)
+    graph.gfpush_device(sample, coef, rmax, k, check=True)
+    st = graph.cumulative_stats(reset=True)
+    _, _, _, ost = og.gfpush(ip, ix, sample.cpu().numpy(), coef, rmax, k)
+    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * ost.edges_pushed
+    assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
+    assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
+    del graph
+    torch.cuda.empty_cache()
 
 
 def test_gfpush_full_size_idempotent(reddit_shape):

@@ -201,8 +201,7 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
-    DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
-                "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 1,
+    DEFAULTS = {"push_cluster": 1, "push_cluster_probe": 8, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
                 "push_smem_probe": 2, "push_max_ctas": 0}
 
     def __init__(self, **kv):
@@ -219,22 +218,25 @@ class _tuning:
             _lib.set_tuning(k, self.DEFAULTS[k])
 
 
-# Every tier of HBM-mode GFPush: plain slabs / the shared-memory hash in front of the slabs (default; with a
-# probe limit of 1 and 2 most nodes spill to the slab, so both residencies and their mix are exercised) /
-# the L2 hash tier with one CTA per source, with clusters of 2..16 CTAs per source over DSMEM, and with a table
-# so small that most sources are handed over to the slabs.
+# Every tier of HBM-mode GFPush: plain slabs / the shared-memory table in front of the slabs (with a probe limit of 1
+# and 2 most nodes spill to the slab, so both residencies and their mix are exercised) / the cluster kernel with one
+# CTA per source and with clusters of 2..16 CTAs exchanging pushed edges through L2, with hub entries shared by the
+# whole cluster, and with a probe limit so small that many sources are handed over to the slab kernel.
 TIERS = {
-    "slab": dict(push_smem_hash=0),
-    "smem": dict(push_smem_hash=2),
-    "smem_probe1": dict(push_smem_hash=2, push_smem_probe=1),
-    "smem_probe2": dict(push_smem_hash=2, push_smem_probe=2),
-    "l2hash_g1": dict(push_hash=1, push_cluster=1, push_pilot=16),
-    "l2hash_g2": dict(push_hash=1, push_cluster=2, push_pilot=16),
-    "l2hash_g4": dict(push_hash=1, push_cluster=4, push_pilot=16),
-    "l2hash_g8": dict(push_hash=1, push_cluster=8, push_pilot=16, push_smem_hash=0),
-    "l2hash_g16": dict(push_hash=1, push_cluster=16, push_pilot=16),
-    "l2hash_g1_tiny": dict(push_hash=1, push_cluster=1, push_hash_slots=2048, push_pilot=16),
-    "l2hash_g4_tiny": dict(push_hash=1, push_cluster=4, push_hash_slots=2048, push_pilot=16, push_smem_hash=0),
+    "slab": dict(push_cluster=0, push_smem_hash=0),
+    "smem": dict(push_cluster=0, push_smem_hash=2),
+    "smem_probe1": dict(push_cluster=0, push_smem_hash=2, push_smem_probe=1),
+    "smem_probe2": dict(push_cluster=0, push_smem_hash=2, push_smem_probe=2),
+    "cluster_auto": dict(push_cluster=1),
+    "cluster_g1": dict(push_cluster=-1),
+    "cluster_g2": dict(push_cluster=2),
+    "cluster_g4": dict(push_cluster=4),
+    "cluster_g8": dict(push_cluster=8),
+    "cluster_g16": dict(push_cluster=16),
+    "cluster_g4_hubs": dict(push_cluster=4, push_hub_deg=8),
+    "cluster_g1_redo": dict(push_cluster=-1, push_cluster_probe=1),
+    "cluster_g2_redo": dict(push_cluster=2, push_cluster_probe=1),
+    "cluster_g4_few": dict(push_cluster=4, push_max_clusters=3),
 }
 
 
@@ -262,12 +264,14 @@ def test_gfpush_tiers_give_the_oracle_rows_and_counters(tier):
     assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
     assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
     assert st["sources"] == len(src)
-    if not kv.get("push_hash"):
-        assert st["hash_sources"] == 0 and st["hash_fallbacks"] == 0
-    elif kv.get("push_hash_slots"):
-        assert st["hash_fallbacks"] > 0 and st["hash_sources"] + st["hash_fallbacks"] == len(src) - 16
+    if kv.get("push_cluster") == 0:
+        assert st["cluster_sources"] == 0 and st["redo_sources"] == 0
     else:
-        assert st["hash_sources"] > 0.5 * len(src)
+        assert st["cluster_sources"] + st["redo_sources"] == len(src)
+        if "redo" in tier:
+            assert 0 < st["redo_sources"] < len(src), st
+        else:
+            assert st["redo_sources"] == 0, st
     assert st2["sources"] == 2 * len(src)
     assert abs(st2["edges_pushed"] - 2 * ost.edges_pushed) <= 2e-6 * ost.edges_pushed
     for (ac, av), (bc, bv) in zip(og.rows_as_sets(col, val, 32), og.rows_as_sets(col2, val2, 32)):
@@ -278,11 +282,11 @@ def test_gfpush_tiers_give_the_oracle_rows_and_counters(tier):
 @pytest.mark.parametrize("probe", [1, 3, 16])
 @pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("pubmed", "ppr"), ("citeseer", "single")])
 def test_gfpush_smem_hash_matches_reference_golden(name, mode, probe):
-    """Real graphs through the shared-memory hash tier in HBM mode (Cora's ppr support is the whole component)."""
+    """Real graphs through the shared-memory table tier in HBM mode (Cora's ppr support is the whole component)."""
     indptr, indices = load_graph(name)
     z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
     K, rmax = int(z["K"]), float(z["rmax"])
-    with _tuning(push_smem_hash=2, push_smem_probe=probe):
+    with _tuning(push_cluster=0, push_smem_hash=2, push_smem_probe=probe):
         g = _graph(indptr, indices, scratch_mode=HBM)
         row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
     worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
@@ -290,37 +294,90 @@ def test_gfpush_smem_hash_matches_reference_golden(name, mode, probe):
 
 
 @pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("citeseer", "avg"), ("pubmed", "ppr"), ("pubmed", "single")])
-@pytest.mark.parametrize("cluster", [1, 4])
-def test_gfpush_hash_tier_matches_reference_golden(name, mode, cluster):
-    """Real graphs through the hash tier (forced: these graphs are small enough that auto keeps the slabs)."""
+@pytest.mark.parametrize("cluster", [-1, 2, 16])
+def test_gfpush_cluster_kernel_matches_reference_golden(name, mode, cluster):
+    """Real graphs through the cluster kernel (forced: these graphs are small enough that auto picks the dense mode)."""
     indptr, indices = load_graph(name)
     z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
     K, rmax = int(z["K"]), float(z["rmax"])
-    with _tuning(push_hash=1, push_cluster=cluster, push_pilot=8):
+    with _tuning(push_cluster=cluster):
         g = _graph(indptr, indices, scratch_mode=HBM)
         g.cumulative_stats(reset=True)
         row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
         st = g.cumulative_stats()
-    assert st["hash_sources"] + st["hash_fallbacks"] == len(z["node_idx"]) - 8
-    assert st["hash_sources"] > 0
+        assert g.last_stats()["cluster_size"] == abs(cluster)
+    assert st["cluster_sources"] == len(z["node_idx"]) and st["redo_sources"] == 0
     worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
     assert worst < 1e-11, worst
+    _, _, _, ost = og.gfpush(indptr, indices, z["node_idx"], z["coef"], rmax, K)
+    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * max(ost.edges_pushed, 1)
+    assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
+    assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
 
 
 @pytest.mark.parametrize("name", ["path8", "star33", "isolated", "dangling"])
-def test_gfpush_hash_tier_tiny_graphs(name):
-    """Dangling nodes, K > support, degree-1 nodes: the edge cases of graph.h:91-93,113,121 on the hash tier."""
+@pytest.mark.parametrize("cluster", [-1, 2, 8])
+def test_gfpush_cluster_kernel_tiny_graphs(name, cluster):
+    """Dangling nodes, K > support, degree-1 nodes: the edge cases of graph.h:91-93,113,121 on the cluster kernel."""
     z = np.load(os.path.join(GOLDEN, f"tiny_{name}.npz"))
-    reps = 6                                       # enough sources for the pilot + the tier
+    reps = 6
     src = np.tile(z["node_idx"], reps)
-    with _tuning(push_hash=1, push_cluster=2, push_pilot=1):
+    with _tuning(push_cluster=cluster, push_hub_deg=4):
         g = _graph(z["indptr"], z["indices"], scratch_mode=HBM)
         for tag in sorted({k.split("/")[0] for k in z.files if "/" in k}):
             K, rmax, coef = int(z[f"{tag}/K"]), float(z[f"{tag}/rmax"]), z[f"{tag}/coef"]
             g.cumulative_stats(reset=True)
             row, col, val = _run(g, src, coef, rmax, K)
             st = g.cumulative_stats()
-            assert st["hash_sources"] == len(src) - 1, (tag, st)
+            assert st["cluster_sources"] == len(src), (tag, st)
             check_topk_rows(z["indptr"], z["indices"], src, coef, rmax, K, col, val, row=row)
             ref_filled = np.tile((z[f"{tag}/value"].reshape(-1, K) > 0).sum(1), reps)
             np.testing.assert_array_equal((val.reshape(-1, K) > 0).sum(1), ref_filled)
+
+
+def test_gfpush_device_path_surfaces_device_side_errors():
+    """gp_gfpush_device returns before the kernels run: a source id outside the graph must still raise, either at once
+    (check=True) or at the next check_errors(), and must not poison later calls."""
+    import torch
+    from grandplus_b200._lib import GPError
+    indptr, indices = load_graph("cora")
+    coef = og.coef_for("ppr", 4, 0.2)
+    for scratch in (SMEM, HBM):
+        g = _graph(indptr, indices, scratch_mode=scratch)
+        bad = torch.tensor([0, 5, 99999, 7], dtype=torch.int32, device="cuda")
+        with pytest.raises(GPError):
+            g.gfpush_device(bad, coef, 1e-5, 8, check=True)
+        row, col, val, _ = g.gfpush_device(bad, coef, 1e-5, 8)        # asynchronous: returns ...
+        g.gfpush_device(bad[:2].contiguous(), coef, 1e-5, 8)          # ... and the flag survives a later good call
+        with pytest.raises(GPError):
+            g.check_errors()
+        assert float(val[2].abs().sum()) == 0.0                       # the refused row reads (0, 0, 0.0)
+        good = torch.tensor([0, 5, 7], dtype=torch.int32, device="cuda")
+        g.gfpush_device(good, coef, 1e-5, 8, check=True)              # clean again
+
+
+def test_gfpush_two_streams_on_one_handle_are_ordered():
+    """A push on another stream must wait for the previous push of the handle (they share the control block, the
+    coefficient array and the scratch): host-buffer call, device call on a side stream, device call on the default
+    stream, no synchronisation in between -- all three must give the oracle's rows."""
+    import torch
+    from grandplus_b200 import synth
+    indptr, indices = synth.powerlaw_csr(60_000, 700_000, seed=5)
+    indptr, indices = indptr.numpy(), indices.numpy()
+    coef_a, coef_b = og.coef_for("ppr", 6, 0.05), og.coef_for("avg", 3, 0.2)
+    src = synth.sources(60_000, 600, seed=9)
+    g = _graph(indptr, indices)
+    side = torch.cuda.Stream()
+    d_src = src.cuda()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        ra = g.gfpush_device(d_src, coef_a, 1e-5, 32)
+    rb = g.gfpush_device(d_src, coef_b, 1e-5, 32)
+    with torch.cuda.stream(side):
+        rc = g.gfpush_device(d_src, coef_a, 1e-5, 32)
+    torch.cuda.synchronize()
+    g.check_errors()
+    for (row, col, val, _), coef in ((ra, coef_a), (rb, coef_b), (rc, coef_a)):
+        worst = check_topk_rows(indptr, indices, src.numpy(), coef, 1e-5, 32, col.cpu().numpy().ravel(),
+                                val.cpu().numpy().ravel(), row=row.cpu().numpy().ravel(), max_rows=60)
+        assert worst < 1e-11

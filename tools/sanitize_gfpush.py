@@ -1,5 +1,6 @@
 import sys, numpy as np
-sys.path.insert(0, '/root/repo')
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from grandplus_b200 import _lib, synth
 from grandplus_b200.precompute import propagation
 from oracle import gfpush as og
@@ -10,8 +11,10 @@ src = synth.sources(20_000, 64, seed=4).numpy()
 coef = og.coef_for("ppr", 5, 0.1)
 """Small GFPush run for compute-sanitizer (memcheck / racecheck) over every residue-table mode:
     compute-sanitizer --tool racecheck python tools/sanitize_gfpush.py"""
-for kv in (dict(push_smem_hash=2, push_smem_probe=4), dict(push_smem_hash=2, push_smem_probe=1), dict(push_smem_hash=0),
-           dict(scratch=1)):
+for kv in (dict(push_cluster=0, push_smem_hash=2, push_smem_probe=4), dict(push_cluster=0, push_smem_hash=2, push_smem_probe=1),
+           dict(push_cluster=0, push_smem_hash=0), dict(scratch=1),
+           dict(push_cluster=-1), dict(push_cluster=2), dict(push_cluster=4, push_hub_deg=8), dict(push_cluster=16),
+           dict(push_cluster=2, push_cluster_probe=1)):
     scratch = kv.pop("scratch", 2)
     for k, v in kv.items(): _lib.set_tuning(k, v)
     g = propagation.Graph(indptr, indices, 0); g.configure(scratch_mode=scratch)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Sweep GFPush tier settings on one workload (GPU box).  Prints rows/s per configuration.
 
-    python tools/sweep_gfpush.py reddit "push_hash=0" "push_cluster=1" "push_cluster=2,push_load_pct=60" ...
+    python tools/sweep_gfpush.py reddit "push_cluster=0" "push_cluster=2" "push_cluster=4,push_hub_deg=128" ...
 """
 import os
 import sys
@@ -16,13 +16,13 @@ import bench  # noqa: E402
 from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
-DEFAULTS = {"push_hash": 0, "push_cluster": 0, "push_hash_slots": 0, "push_pilot": 256, "push_load_pct": 60,
-            "push_list_div": 8, "push_l2_mb": 48, "push_hash_block": 1024, "push_max_clusters": 0, "push_smem_hash": 1, "push_smem_probe": 2, "push_max_ctas": 0}
+DEFAULTS = {"push_cluster": 1, "push_cluster_probe": 8, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+            "push_smem_probe": 2, "push_max_ctas": 0}
 
 
 def main():
     name = sys.argv[1]
-    configs = sys.argv[2:] or ["push_hash=0", "push_hash=1"]
+    configs = sys.argv[2:] or ["push_cluster=0", "push_cluster=1"]
     steps = int(os.environ.get("SWEEP_STEPS", "4"))
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -64,15 +64,16 @@ def main():
         torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / 1e3
         st = graph.cumulative_stats(reset=True)
-        print(f"{name} S={S} {cfg:40s} rows/s={S * steps / t:12.0f}  edges/s={st['edges_pushed'] / t / 1e9:7.2f}G  "
-              f"hash={st['hash_sources']} redo={st['hash_fallbacks']} sup/src={st['support_total'] / max(st['sources'], 1):.0f} "
-              f"scratch={st['scratch_bytes'] / 1e6:.0f}MB", flush=True)
+        ls = graph.last_stats()
+        print(f"{name} S={S} {cfg:44s} rows/s={S * steps / t:12.0f}  edges/s={st['edges_pushed'] / t / 1e9:7.2f}G  "
+              f"G={ls['cluster_size']} ctas={ls['ctas']} cluster={st['cluster_sources']} redo={st['redo_sources']} "
+              f"sup/src={st['support_total'] / max(st['sources'], 1):.0f} scratch={ls['scratch_bytes'] / 1e6:.0f}MB", flush=True)
         ph = graph.phase_cycles(reset=True)
         if ph["resident"]:
-            names = ph.keys() if st["hash_sources"] else ("fetch", "expand", "settle", "merge", "topk", "wide_expand", "wide_settle")
+            # CTA time per source: resident cycles of all CTAs / sources (a cluster of G CTAs spends G x its latency)
             us = ph["resident"] / 1965.0 / max(st["sources"], 1)
             print(f"    {us:.0f} us of CTA time per source; % by phase: " +
-                  " ".join(f"{n}={100.0 * v / ph['resident']:.1f}" for n, v in zip(names, ph.values()) if n != "-"), flush=True)
+                  " ".join(f"{n}={100.0 * v / ph['resident']:.1f}" for n, v in ph.items() if n != "resident"), flush=True)
     for k, v in DEFAULTS.items():
         _lib.set_tuning(k, v)
 
