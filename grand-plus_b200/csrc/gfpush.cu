@@ -43,7 +43,8 @@ int g_push_smem_hash = 1;     // "push_smem_hash": shared-memory residue table i
 int g_push_smem_probe = 2;    // "push_smem_probe": 4-key buckets tried before a node is sent to the slab
 int g_push_cluster = 1;       // "push_cluster": the cluster kernel (gfpush_cluster.cu) for graphs beyond the dense shared-memory mode:
                               // 0 off, 1 auto (cluster size from the expected support), 2/4/8/16 = that cluster size, -1 = one CTA
-int g_push_cluster_probe = 8; // "push_cluster_probe": 4-key buckets tried before a source is handed to the slab kernel
+int g_push_cluster_probe = 128;   // "push_cluster_probe": 4-key buckets tried before a source is handed to the slab kernel
+                                  // (at the loads the planner aims at the longest probe sequence is a few buckets)
 int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree are expanded by the whole cluster (0 = 64 x G)
 int g_push_max_clusters = 0;  // "push_max_clusters": cap on the resident clusters (0 = all the device schedules); scaling experiments
 int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments

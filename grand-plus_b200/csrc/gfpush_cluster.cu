@@ -42,20 +42,36 @@ constexpr int kBuckets = kClusterSlots / 4;   // 4-key buckets: one 16-byte shar
 constexpr int kEmpty = -1;
 constexpr int kEdgeUnroll = 4;
 
+constexpr int kCandCap = 1024;   // nodes per level (and CTA) whose degree code allows a push; more are handled inline
+constexpr int kRankCap = 64;     // the radix select refines until the boundary bucket is this small, then rank-counts it
+
 struct CSmem {
     unsigned off[CB + 1];      // exclusive scan of the tile's degrees, off[CB] = total
     int start[CB];
     double add[CB];
     unsigned warp_scan[CB / 32 + 1];
-    unsigned hist[kHistBins];
-    unsigned long long bkey[kBucketCap];
-    int bid[kBucketCap];
+    double wtau[CB / 32];      // top-k pre-filter: per-warp lower bounds of the K-th largest reserve
+    union {
+        struct {               // top-k
+            unsigned hist[kHistBins];
+            unsigned long long bkey[kBucketCap];
+            int bid[kBucketCap];
+        } sel;
+        struct {               // settle: candidates for a push
+            double r[kCandCap];
+            unsigned key[kCandCap];
+        } cand;
+    };
     unsigned cnt[kClusterMaxG];      // entries this CTA appended to the stream of each destination (this level)
+    unsigned inbox[kClusterMaxG];    // entries every sender appended to MY stream (written by the senders before barrier #2)
     unsigned pre[kClusterMaxG + 1];  // exchange / final select: prefix sums over the senders
     long long it;                    // (first CTA) the cluster's current source
     int n_push;                      // local push-list entries of this level
+    int n_sel;                       // settle candidates
     int n_out, n_bucket, n_cand;
     int sel_bin, sel_above, sel_inbin;
+    int seed_slot;
+    int full;                        // a probe sequence ran out: this source goes to the slab kernel, stop probing
     // cluster-wide state, valid in the first CTA's copy
     unsigned c_push[2];              // push-list entries of all CTAs, by level parity
     unsigned c_hub[2];               // hub entries, by level parity
@@ -95,63 +111,72 @@ __device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int
 // invoked once per radix pass).  emit_fn(position, id, value) receives them in arbitrary order; returns their number.
 // MSD radix select on the fp64 bit pattern as in gfpush.cu.  Every thread of the CTA must call it.
 template <class Each, class Emit>
-__device__ __forceinline__ int block_topk(CSmem &sm, const int K, Each each, Emit emit_fn) {
+__device__ __forceinline__ int block_topk(CSmem &sm, const int K, const bool small, Each each, Emit emit_fn) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < kHistBins; i += CB) sm.hist[i] = 0;
     if (tid == 0) { sm.n_out = 0; sm.n_bucket = 0; }
-    __syncthreads();
-    each([&](double x, int) { atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u); });
-    __syncthreads();
-    int shift = 52, bits = 11;
-    unsigned long long prefix = 0;   // value of key >> (shift + bits) shared by the boundary bucket
-    int kk = K;
-    bool first = true;
-    unsigned long long Tkey = 0;
-    int want_bucket = 0;
-    for (;;) {
-        const unsigned total = select_bin_generic<CB>(sm.hist, sm.warp_scan, 1 << bits, kk, first, &sm.sel_bin,
-                                                      &sm.sel_above, &sm.sel_inbin);
-        if (first) kk = min(kk, (int)total);   // k = min(K, #positive): graph.h:113 + the v > 0 filter of :121
-        if (kk == 0) { want_bucket = 0; Tkey = ~0ull; break; }
-        const int bin = sm.sel_bin, above = sm.sel_above, inbin = sm.sel_inbin;
-        Tkey = (prefix << bits) | (unsigned long long)bin;
-        want_bucket = kk - above;
-        if (inbin <= kBucketCap || shift == 0) break;
-        kk = want_bucket; first = false; prefix = Tkey;
+    int want_bucket = K;
+    if (small) {
+        // at most kBucketCap items in all (uniform): rank-count them directly
         __syncthreads();
-        for (int i = tid; i < kHistBins; i += CB) sm.hist[i] = 0;
-        __syncthreads();
-        const int nshift = shift >= 11 ? shift - 11 : 0;
-        const int nbits = shift >= 11 ? 11 : shift;
-        each([&](double x, int) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-            if ((key >> shift) == prefix) atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
-        });
-        shift = nshift; bits = nbits;
-        __syncthreads();
-    }
-    each([&](double x, int id) {
-        const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-        const unsigned long long t = key >> shift;
-        if (t > Tkey) {
-            emit_fn(atomicAdd(&sm.n_out, 1), id, x);
-        } else if (t == Tkey) {
+        each([&](double x, int id) {
             const int pos = atomicAdd(&sm.n_bucket, 1);
-            if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = id; }
+            sm.sel.bkey[pos] = (unsigned long long)__double_as_longlong(x); sm.sel.bid[pos] = id;
+        });
+    } else {
+        for (int i = tid; i < kHistBins; i += CB) sm.sel.hist[i] = 0;
+        __syncthreads();
+        each([&](double x, int) { atomicAdd(&sm.sel.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u); });
+        __syncthreads();
+        int shift = 52, bits = 11;
+        unsigned long long prefix = 0;   // value of key >> (shift + bits) shared by the boundary bucket
+        int kk = K;
+        bool first = true;
+        unsigned long long Tkey = 0;
+        for (;;) {
+            const unsigned total = select_bin_generic<CB>(sm.sel.hist, sm.warp_scan, 1 << bits, kk, first, &sm.sel_bin,
+                                                          &sm.sel_above, &sm.sel_inbin);
+            if (first) kk = min(kk, (int)total);   // k = min(K, #positive): graph.h:113 + the v > 0 filter of :121
+            if (kk == 0) { want_bucket = 0; Tkey = ~0ull; break; }
+            const int bin = sm.sel_bin, above = sm.sel_above, inbin = sm.sel_inbin;
+            Tkey = (prefix << bits) | (unsigned long long)bin;
+            want_bucket = kk - above;
+            if (inbin <= kRankCap || shift == 0) break;
+            kk = want_bucket; first = false; prefix = Tkey;
+            __syncthreads();
+            for (int i = tid; i < kHistBins; i += CB) sm.sel.hist[i] = 0;
+            __syncthreads();
+            const int nshift = shift >= 11 ? shift - 11 : 0;
+            const int nbits = shift >= 11 ? 11 : shift;
+            each([&](double x, int) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+                if ((key >> shift) == prefix) atomicAdd(&sm.sel.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
+            });
+            shift = nshift; bits = nbits;
+            __syncthreads();
         }
-    });
+        each([&](double x, int id) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+            const unsigned long long t = key >> shift;
+            if (t > Tkey) {
+                emit_fn(atomicAdd(&sm.n_out, 1), id, x);
+            } else if (t == Tkey) {
+                const int pos = atomicAdd(&sm.n_bucket, 1);
+                if (pos < kBucketCap) { sm.sel.bkey[pos] = key; sm.sel.bid[pos] = id; }
+            }
+        });
+    }
     __syncthreads();
     {
         // rank-count the boundary bucket: keep its `want_bucket` largest (ties: lower position first)
         const int nb = min(sm.n_bucket, kBucketCap);
         for (int i = tid; i < nb; i += CB) {
-            const unsigned long long ki = sm.bkey[i];
+            const unsigned long long ki = sm.sel.bkey[i];
             int rank = 0;
             for (int q = 0; q < nb; q++) {
-                const unsigned long long kq = sm.bkey[q];
+                const unsigned long long kq = sm.sel.bkey[q];
                 rank += (kq > ki) || (kq == ki && q < i);
             }
-            if (rank < want_bucket) emit_fn(atomicAdd(&sm.n_out, 1), sm.bid[i], __longlong_as_double((long long)ki));
+            if (rank < want_bucket) emit_fn(atomicAdd(&sm.n_out, 1), sm.sel.bid[i], __longlong_as_double((long long)ki));
         }
     }
     __syncthreads();
@@ -162,6 +187,7 @@ template <int G>
 __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPushParams P) {
     constexpr int LOGG = Log2<G>::v;
     constexpr int kOwnerShift = G > 1 ? 32 - LOGG : 31;   // hash >> kOwnerShift = owning CTA (unused when G == 1)
+    constexpr int kBucketShift = 32 - LOGG - 12;          // the 12 hash bits below the owner bits pick the bucket
     __shared__ CSmem sm;
     extern __shared__ double s_vals[];                      // [kClusterSlots] next-level residues
     int *s_keys = reinterpret_cast<int *>(s_vals + kClusterSlots);   // [kClusterSlots] packed node, kEmpty = free
@@ -194,10 +220,9 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
 #pragma unroll
     for (int j = 0; j < SPT; j++) rsv[j] = 0.0;
     if (tid == 0) {
-        sm.c_push[0] = sm.c_push[1] = 0; sm.c_hub[0] = sm.c_hub[1] = 0; sm.c_flags = 0; sm.n_push = 0;
+        sm.c_push[0] = sm.c_push[1] = 0; sm.c_hub[0] = sm.c_hub[1] = 0; sm.c_flags = 0; sm.n_push = 0; sm.n_sel = 0; sm.full = 0;
         for (int i = 0; i < 8; i++) sm.ph[i] = 0;
     }
-    if (tid < kClusterMaxG) sm.cnt[tid] = 0;
     unsigned long long st_edges = 0, st_sources = 0, st_cluster = 0, st_redo = 0;   // thread 0 only
     unsigned st_frontier = 0, st_support = 0;                                         // every thread, reduced at the end
     const long long t_begin = clock64();
@@ -206,7 +231,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
 
     for (;;) {
         if (rank == 0 && tid == 0) sm.it = (long long)atomicAdd(P.queue, 1ull);
-        csync();
+        csync();   // #B
         const long long it = ldr->it;
         if (it >= P.S) break;
         const int src = P.node_idx[it];
@@ -230,83 +255,90 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
             const unsigned cap = (1u << (32 - P.idbits)) - 2u;
             src_packed = (int)((unsigned)src | (min((unsigned)src_rec.y, cap) << P.idbits));
         }
-        // level 0: residue = {src: 1} (graph.h:80); the source's owner seeds its (empty) table
+        bool ovf = false;
+        // A push-list entry {start, len, add}: the first CB of a level stay in the tile arrays of the expansion.
+        auto add_entry = [&](int e_start, unsigned e_len, double e_add, int par) {
+            if (G > 1 && e_len >= (unsigned)P.hub_min_deg) {
+                const unsigned p = atomicAdd(&ldr->c_hub[par], 1u);
+                if (p < (unsigned)P.capHub) { hub_start[p] = e_start; hub_deg[p] = (int)e_len; hub_add[p] = e_add; }
+                else ovf = true;
+            } else {
+                const int p = atomicAdd(&sm.n_push, 1);
+                if (p < CB) { sm.start[p] = e_start; sm.off[p] = e_len; sm.add[p] = e_add; }
+                else if (p < P.capP) { push_start[p] = e_start; push_len[p] = (int)e_len; push_add[p] = e_add; }
+                else ovf = true;
+            }
+        };
+        // Exact push decision of a node whose degree code allows it (graph.h:91-95); fetches its {start, degree} record.
+        auto consider = [&](unsigned key, double r, int par) {
+            const int2 rec = __ldg(P.node_rec + (key & idmask));
+            const unsigned d = (unsigned)rec.y;
+            if (d == 0) add_entry(-1, 1u, r, par);                                     // graph.h:91-93: back to the source
+            else if (r >= P.rmax * (double)d) add_entry(rec.x, d, r / (double)d, par);   // graph.h:94-95
+        };
+        // ------------------------------------------------------------------ level 0 (graph.h:80-82)
+        // residue = {src: 1}: the reserve of the source's slot gets coef[0], and the source's adjacency is expanded by
+        // the whole cluster (every CTA takes a 1/G slice) without a settle pass or a barrier.
+        const unsigned hsrc = hash_node((unsigned)src);
+        const bool mine = (G > 1 ? hsrc >> kOwnerShift : 0u) == rank;
+        const unsigned deg0 = (unsigned)src_rec.y;
+        const bool push0 = P.L > 1 && (deg0 == 0 || 1.0 >= P.rmax * (double)deg0);
         if (tid == 0) {
             if (rank == 0) { st_sources++; st_cluster++; }
-            const unsigned h = hash_node((unsigned)src);
-            const unsigned owner = G > 1 ? h >> kOwnerShift : 0u;
-            if (owner == rank) {
-                const int slot = find_slot(s_keys, (h >> (32 - LOGG - 12)) & (kBuckets - 1), src_packed, 1);
-                s_vals[slot] = 1.0;
-            }
-        }
-        __syncthreads();
-        GPC_PHASE(0);
-
-        for (int level = 0; level < P.L; level++) {   // graph.h:83 (+ the last level, :104-110)
-            const int par = level & 1;
-            const bool will_push = level < P.L - 1;
-            const double c = P.coef[level];
-            // ---------------------------------------------------------------- settle (graph.h:85-93,102)
-            bool ovf = false;
-#pragma unroll
-            for (int j = 0; j < SPT; j++) {
-                const int slot = j * CB + tid;
-                const double r = s_vals[slot];
-                if (r != 0.0) {
-                    s_vals[slot] = 0.0;
-                    rsv[j] += c * r;                                   // graph.h:90 / :106
-                    src_front++;
-                    if (will_push) {
-                        const unsigned key = (unsigned)s_keys[slot];
-                        const unsigned code = has_code ? key >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
-                        if (r >= P.rmax * (double)code) {              // necessary for graph.h:94; exact test below
-                            const int2 rec = __ldg(P.node_rec + (key & idmask));
-                            const unsigned d = (unsigned)rec.y;
-                            int e_start = -1; unsigned e_len = 0; double e_add = r;
-                            if (d == 0) { e_len = 1; }                                             // graph.h:91-93: back to the source
-                            else if (r >= P.rmax * (double)d) { e_start = rec.x; e_len = d; e_add = r / (double)d; }   // graph.h:94-95
-                            if (e_len) {
-                                if (G > 1 && e_len >= (unsigned)P.hub_min_deg) {
-                                    const unsigned p = atomicAdd(&ldr->c_hub[par], 1u);
-                                    if (p < (unsigned)P.capHub) { hub_start[p] = e_start; hub_deg[p] = (int)e_len; hub_add[p] = e_add; }
-                                    else ovf = true;
-                                } else {
-                                    const int p = atomicAdd(&sm.n_push, 1);
-                                    if (p < P.capP) { push_start[p] = e_start; push_len[p] = (int)e_len; push_add[p] = e_add; }
-                                    else ovf = true;
-                                }
-                            }
-                        }
-                    }
+            if (mine) sm.seed_slot = find_slot(s_keys, (hsrc >> kBucketShift) & (kBuckets - 1), src_packed, 1);   // empty table
+            int n0 = 0;
+            if (push0) {
+                if (deg0 == 0) {
+                    if (rank == 0) { sm.start[0] = -1; sm.off[0] = 1u; sm.add[0] = 1.0; n0 = 1; }
+                } else {
+                    const unsigned lo = (unsigned)((unsigned long long)deg0 * rank / G), hi = (unsigned)((unsigned long long)deg0 * (rank + 1) / G);
+                    if (hi > lo) { sm.start[0] = src_rec.x + (int)lo; sm.off[0] = hi - lo; sm.add[0] = 1.0 / (double)deg0; n0 = 1; }
                 }
             }
-            if (ovf) atomicOr(&ldr->c_flags, 1u);
-            __syncthreads();
-            GPC_PHASE(2);
-            if (!will_push) break;
-            if (G > 1) {
-                if (tid == 0 && sm.n_push) atomicAdd(&ldr->c_push[par], (unsigned)sm.n_push);
-                csync();   // #1: every CTA's push list and the hub list of this level are complete
+            sm.n_push = n0;
+        }
+        __syncthreads();
+        if (mine) {
+            const int slot = sm.seed_slot;
+            if ((slot & (CB - 1)) == tid) {
+                const double c0 = P.coef[0];
+#pragma unroll
+                for (int j = 0; j < SPT; j++)
+                    rsv[j] += j == slot / CB ? c0 : 0.0;   // graph.h:90 at level 0 (written so that rsv[] stays in registers)
+                src_front++;
             }
-            const int n_local = min((long long)sm.n_push, P.capP);
-            const int n_hub = G > 1 ? (int)min(ldr->c_hub[par], (unsigned)P.capHub) : 0;
-            const unsigned n_all = G > 1 ? ldr->c_push[par] + ldr->c_hub[par] : (unsigned)n_local;
-            if (n_all == 0) break;   // nothing pushes: every later residue is zero (the reserve is complete)
-            if (G > 1) {
-                if (rank == 0 && tid == 0) { sm.c_push[par ^ 1] = 0; sm.c_hub[par ^ 1] = 0; }
-                if (tid < G) sm.cnt[tid] = 0;   // the receivers finished reading them before barrier #1
+        }
+        GPC_PHASE(0);
+
+        for (int level = 0; level < P.L - 1; level++) {   // graph.h:83
+            const int par = level & 1;
+            int n_local, n_hub = 0;
+            if (level == 0) {
+                if (!push0) break;
+                n_local = sm.n_push;
+            } else {
+                if (G > 1) {
+                    if (tid == 0 && sm.n_push) atomicAdd(&ldr->c_push[par], (unsigned)sm.n_push);
+                    csync();   // #1: every CTA's push list and the hub list of this level are complete
+                }
+                n_local = min((long long)sm.n_push, P.capP);
+                if (G > 1) n_hub = (int)min(ldr->c_hub[par], (unsigned)P.capHub);
+                const unsigned n_all = G > 1 ? ldr->c_push[par] + ldr->c_hub[par] : (unsigned)n_local;
+                if (n_all == 0) break;   // nothing pushes: every later residue is zero (the reserve is complete)
+                if (G > 1 && rank == 0 && tid == 0) { sm.c_push[par ^ 1] = 0; sm.c_hub[par ^ 1] = 0; }
             }
+            if (G > 1 && tid < G) sm.cnt[tid] = 0;
             // ---------------------------------------------------------------- expand (graph.h:94-100)
-            ovf = false;
             const int n_items = n_local + n_hub;
             for (int base = 0; base < n_items; base += CB) {
                 const int j = base + tid;
                 unsigned len = 0;
                 int start = 0;
                 double add = 0.0;
-                if (j < n_local) { start = push_start[j]; len = (unsigned)push_len[j]; add = push_add[j]; }
-                else if (j < n_items) {   // this CTA's slice of a hub entry
+                if (j < n_local) {
+                    if (base == 0) { start = sm.start[tid]; len = sm.off[tid]; add = sm.add[tid]; }   // written by settle
+                    else { start = push_start[j]; len = (unsigned)push_len[j]; add = push_add[j]; }
+                } else if (j < n_items) {   // this CTA's slice of a hub entry
                     const int h = j - n_local;
                     const unsigned d = (unsigned)__ldcg(hub_deg + h);
                     const unsigned lo = (unsigned)((unsigned long long)d * rank / G), hi = (unsigned)((unsigned long long)d * (rank + 1) / G);
@@ -338,13 +370,13 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
 #pragma unroll
                         for (int q = 0; q < kEdgeUnroll; q++) {
                             slot[q] = 0;
-                            if (ok[q]) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> 20) & (kBuckets - 1), vp[q], P.max_probe);
+                            if (ok[q] && !*(volatile int *)&sm.full) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> kBucketShift) & (kBuckets - 1), vp[q], P.max_probe);
                         }
 #pragma unroll
                         for (int q = 0; q < kEdgeUnroll; q++) {
                             if (ok[q]) {
                                 if (slot[q] >= 0) atomicAdd(s_vals + slot[q], av[q]);   // graph.h:98
-                                else ovf = true;
+                                else { ovf = true; sm.full = 1; }
                             }
                         }
                     } else {
@@ -368,21 +400,25 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                 }
                 __syncthreads();
             }
-            if (ovf) atomicOr(&ldr->c_flags, 1u);
-            if (tid == 0) sm.n_push = 0;
+            if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; }
             GPC_PHASE(1);
             if (G > 1) {
-                csync();   // #2: every stream of this level is complete and visible
+                // tell every receiver how much I sent it, then barrier #2: every stream of this level is complete and visible
+                if (tid < G) cg::this_cluster().map_shared_rank(&sm, tid)->inbox[rank] = min(sm.cnt[tid], (unsigned)P.capX);
+                csync();
                 // ------------------------------------------------------------ exchange: accumulate what was sent to me
-                if (tid < G) sm.pre[tid + 1] = min(cg::this_cluster().map_shared_rank(&sm, tid)->cnt[rank], (unsigned)P.capX);
-                __syncthreads();
-                if (tid == 0) {
-                    sm.pre[0] = 0;
-                    for (int s = 0; s < G; s++) sm.pre[s + 1] += sm.pre[s];
+                if (tid < 32) {
+                    unsigned v = tid < G ? sm.inbox[tid] : 0u, incl = v;
+#pragma unroll
+                    for (int o = 1; o < kClusterMaxG; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    if (tid < G) sm.pre[tid + 1] = incl;
+                    if (tid == 0) sm.pre[0] = 0;
                 }
                 __syncthreads();
                 const unsigned total = sm.pre[G];
-                ovf = false;
                 for (unsigned e0 = tid; e0 < total; e0 += CB * kEdgeUnroll) {
                     int vp[kEdgeUnroll];
                     double av[kEdgeUnroll];
@@ -405,33 +441,97 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         slot[q] = 0;
-                        if (ok[q]) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> (32 - LOGG - 12)) & (kBuckets - 1), vp[q], P.max_probe);
+                        if (ok[q] && !*(volatile int *)&sm.full) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> kBucketShift) & (kBuckets - 1), vp[q], P.max_probe);
                     }
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         if (ok[q]) {
                             if (slot[q] >= 0) atomicAdd(s_vals + slot[q], av[q]);   // graph.h:98
-                            else ovf = true;
+                            else { ovf = true; sm.full = 1; }
                         }
                     }
                 }
-                if (ovf) atomicOr(&ldr->c_flags, 1u);
                 GPC_PHASE(3);
             }
             __syncthreads();
+            // ---------------------------------------------------------------- settle of level + 1 (graph.h:85-93,102; :104-110 for the last)
+            {
+                const int nl = level + 1;
+                const int npar = nl & 1;
+                const bool will_push = nl < P.L - 1;
+                const double c = P.coef[nl];
+#pragma unroll
+                for (int jb = 0; jb < SPT; jb += 8) {
+                    double r8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) r8[u] = s_vals[(jb + u) * CB + tid];
+                    long long any = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) any |= __double_as_longlong(r8[u]);
+                    if (any == 0) continue;   // residues are sums of positive pushes: eight +0.0
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const double r = r8[u];
+                        if (r != 0.0) {
+                            const int slot = (jb + u) * CB + tid;
+                            s_vals[slot] = 0.0;
+                            rsv[jb + u] += c * r;                              // graph.h:90 / :106
+                            src_front++;
+                            if (will_push) {
+                                const unsigned key = (unsigned)s_keys[slot];
+                                const unsigned code = has_code ? key >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
+                                if (r >= P.rmax * (double)code) {              // necessary for graph.h:94; the exact test follows
+                                    const int p = atomicAdd(&sm.n_sel, 1);
+                                    if (p < kCandCap) { sm.cand.key[p] = key; sm.cand.r[p] = r; }
+                                    else consider(key, r, npar);
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (will_push) {
+                    // the few nodes that may push fetch their {start, degree} record in parallel
+                    const int n_sel = min(sm.n_sel, kCandCap);
+                    for (int i = tid; i < n_sel; i += CB) consider(sm.cand.key[i], sm.cand.r[i], npar);
+                    __syncthreads();
+                }
+            }
+            GPC_PHASE(2);
         }
+        if (ovf) atomicOr(&ldr->c_flags, 1u);
         // ------------------------------------------------------------------ top-k, graph.h:111-126
         csync();   // #C: every CTA's overflow flag has landed
         const bool redo = ldr->c_flags != 0;
         if (!redo) { st_frontier += src_front; st_edges += src_edges; }
+        // Pre-filter for the select: every lane's largest (K <= 32) or second largest (K <= 64) reserve is at least the
+        // warp's minimum of them, so at least K reserves of this CTA are >= tau and nothing below tau can be among its K
+        // largest.  The bulk of a source's support (thousands of reserves of a few 1e-7) then never reaches the
+        // histogram, whose few exponent bins would otherwise serialise the shared-memory atomics.
+        double tau = 0.0;
+        if (!redo && P.K <= 64) {
+            double m1 = 0.0, m2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < SPT; j++) {
+                const double x = rsv[j];
+                m2 = fmax(m2, fmin(m1, x));
+                m1 = fmax(m1, x);
+            }
+            double w = P.K <= 32 ? m1 : m2;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) w = fmin(w, __shfl_xor_sync(0xffffffffu, w, o));
+            if (lane == 0) sm.wtau[tid >> 5] = w;
+            __syncthreads();
+            for (int i = 0; i < CB / 32; i++) tau = fmax(tau, sm.wtau[i]);
+        }
         auto each_reg = [&](auto f) {
 #pragma unroll
             for (int j = 0; j < SPT; j++)
-                if (rsv[j] > 0.0) f(rsv[j], (int)((unsigned)s_keys[j * CB + tid] & idmask));
+                if (rsv[j] > 0.0 && rsv[j] >= tau) f(rsv[j], (int)((unsigned)s_keys[j * CB + tid] & idmask));
         };
         if (!redo) {
             if (G == 1) {
-                const int n = block_topk(sm, P.K, each_reg, [&](int pos, int id, double v) {
+                const int n = block_topk(sm, P.K, false, each_reg, [&](int pos, int id, double v) {
                     const long long o = it * P.K + pos;
                     P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
                     if (P.out_val32) P.out_val32[o] = (float)v;
@@ -445,7 +545,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
             } else {
                 int *cand_id = P.cand_id + cta * P.K;
                 double *cand_val = P.cand_val + cta * P.K;
-                const int n = block_topk(sm, P.K, each_reg, [&](int pos, int id, double v) { cand_id[pos] = id; cand_val[pos] = v; });
+                const int n = block_topk(sm, P.K, false, each_reg, [&](int pos, int id, double v) { cand_id[pos] = id; cand_val[pos] = v; });
                 if (tid == 0) sm.n_cand = n;
             }
         }
@@ -462,11 +562,15 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                 if (redo) {
                     if (tid == 0) { P.redo[atomicAdd(P.redo_count, 1ull)] = (int)it; st_redo++; st_sources--; st_cluster--; }
                 } else {
-                    if (tid < G) sm.pre[tid + 1] = (unsigned)cg::this_cluster().map_shared_rank(&sm, tid)->n_cand;
-                    __syncthreads();
-                    if (tid == 0) {
-                        sm.pre[0] = 0;
-                        for (int s = 0; s < G; s++) sm.pre[s + 1] += sm.pre[s];
+                    if (tid < 32) {
+                        unsigned v = tid < G ? (unsigned)cg::this_cluster().map_shared_rank(&sm, tid)->n_cand : 0u, incl = v;
+#pragma unroll
+                        for (int o = 1; o < kClusterMaxG; o <<= 1) {
+                            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += y;
+                        }
+                        if (tid < G) sm.pre[tid + 1] = incl;
+                        if (tid == 0) sm.pre[0] = 0;
                     }
                     __syncthreads();
                     const unsigned total = sm.pre[G];
@@ -479,7 +583,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                             f(__ldcg(P.cand_val + a), __ldcg(P.cand_id + a));
                         }
                     };
-                    const int n = block_topk(sm, P.K, each_cand, [&](int pos, int id, double v) {
+                    const int n = block_topk(sm, P.K, total <= (unsigned)kBucketCap, each_cand, [&](int pos, int id, double v) {
                         const long long o = it * P.K + pos;
                         P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
                         if (P.out_val32) P.out_val32[o] = (float)v;
@@ -496,8 +600,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
             if (redo && tid == 0) { P.redo[atomicAdd(P.redo_count, 1ull)] = (int)it; st_redo++; st_sources--; st_cluster--; }
             if (tid == 0) sm.c_flags = 0;
         }
-        if (tid == 0) sm.n_push = 0;
-        if (tid < kClusterMaxG) sm.cnt[tid] = 0;
+        if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; sm.full = 0; }
         __syncthreads();
         GPC_PHASE(4);
     }

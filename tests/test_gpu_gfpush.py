@@ -201,7 +201,7 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
-    DEFAULTS = {"push_cluster": 1, "push_cluster_probe": 8, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+    DEFAULTS = {"push_cluster": 1, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
                 "push_smem_probe": 2, "push_max_ctas": 0}
 
     def __init__(self, **kv):
@@ -270,6 +270,8 @@ def test_gfpush_tiers_give_the_oracle_rows_and_counters(tier):
         assert st["cluster_sources"] + st["redo_sources"] == len(src)
         if "redo" in tier:
             assert 0 < st["redo_sources"] < len(src), st
+        elif tier == "cluster_g1":   # mean support 13.7 K: a few sources outgrow one CTA's 16 384 slots
+            assert st["redo_sources"] <= 0.1 * len(src), st
         else:
             assert st["redo_sources"] == 0, st
     assert st2["sources"] == 2 * len(src)
