@@ -71,6 +71,8 @@ struct PushParams {
     const int *indptr;
     const int2 *node_rec;  // [n] {indptr[v], degree}: the pair settle needs, as ONE aligned 8-byte load
     const int *indices;
+    const int *packed;     // MODE 2 (nullable): indices with min(degree, cap) in the bits above idbits (gpc_pack_indices)
+    int idbits;            // 32 = no degree code
     int n;
     const int *node_idx;
     long long S;
@@ -268,6 +270,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
     const int tid = threadIdx.x;
     const int lane = gp_lane();
     const long long cta = blockIdx.x;
+    // MODE 0 / 2 read the CSR copy whose entries carry the neighbour's degree code (packed entries are non-negative): the
+    // table key and the frontier-list entry of a slab resident are the packed entry, and settle only fetches a node's
+    // {start, degree} record when the code says it may push (r >= rmax * code)
+    const bool has_code = MODE != 1 && P.packed != nullptr && P.idbits < 32;
+    const unsigned idmask = has_code ? (1u << P.idbits) - 1u : 0xFFFFFFFFu;
+    const int *csr = (MODE != 1 && P.packed != nullptr) ? P.packed : P.indices;
     Tables<false> T;
     T.tab = DENSE ? nullptr : P.tab + cta * (long long)P.n;
     T.pol = l2_policy_evict_last();
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
         if (DENSE) return v;
         if (!table_on) return -1;
         // buckets of four keys (one 16-byte shared-memory read per probe); max_probe buckets are tried
-        unsigned b = (((unsigned)v * 2654435761u) >> 9) & (hmask >> 2);
+        unsigned b = ((((unsigned)v & idmask) * 2654435761u) >> 9) & (hmask >> 2);
         for (int probe = 0; probe < P.max_probe; probe++, b = (b + 1) & (hmask >> 2)) {
             const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * b);
             const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
@@ -332,13 +340,18 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             continue;
         }
         const int epoch = P.epoch_base + (int)it + 1;
+        int src_key = src;   // the source as a table key / CSR entry
+        if (has_code) {
+            const unsigned cap = (1u << (31 - P.idbits)) - 1u;
+            src_key = (int)((unsigned)src | (min((unsigned)(P.indptr[src + 1] - P.indptr[src]), cap) << P.idbits));
+        }
         table_on = SHASH && sm.table_on != 0;   // fixed for the whole source: residency must not change between levels
         // level 0: residue = {src: 1}, reserve = {src: 0} (graph.h:80-81); settle it right away
         if (tid == 0) {
             st_sources++; st_frontier++;
             if (SHASH && sm.table_on) {   // the table is empty: the source claims its home slot; reserve[src] = coef[0]
                 bool claimed;
-                const int h = s_find(src, claimed);
+                const int h = s_find(src_key, claimed);
                 if (DENSE) s_seen[src >> 5] |= 1u << (src & 31);
                 log_id[0] = h; log_val[0] = P.coef[0]; sm.n_log = 1; sm.n_tab = 1;
             } else {
@@ -394,12 +407,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         const unsigned e = e0 + q * BLOCK + lane;
                         ok[q] = e < total;
-                        v[q] = src; add[q] = 0.0;
+                        v[q] = src_key; add[q] = 0.0;
                         if (ok[q]) {
                             const int t = owner_of_edge<BLOCK>(sm.off, e);
                             const int st = sm.start[t];
                             add[q] = sm.val[t];
-                            if (st >= 0) v[q] = __ldcs(P.indices + st + (e - sm.off[t]));  // graph.h:96-97 (streaming: evict first)
+                            if (st >= 0) v[q] = __ldcs(csr + st + (e - sm.off[t]));  // graph.h:96-97 (streaming: evict first)
                         }
                     }
                     bool fresh[kEdgeUnroll];
@@ -417,12 +430,12 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                             fresh[q] = false;
                             if (ok[q]) {
                                 if (h[q] >= 0) { fresh[q] = atomicAdd(s_nxt_dyn + h[q], add[q]) == 0.0; v[q] = ~h[q]; }  // table resident: list entry ~slot
-                                else { fresh[q] = T.add_next(v[q], add[q]); n_spill++; }                                  // slab resident: list entry v
+                                else { fresh[q] = T.add_next((int)((unsigned)v[q] & idmask), add[q]); n_spill++; }   // slab resident: list entry = packed v
                             }
                         }
                     } else {
 #pragma unroll
-                        for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next(v[q], add[q]);
+                        for (int q = 0; q < kEdgeUnroll; q++) fresh[q] = ok[q] && T.add_next((int)((unsigned)v[q] & idmask), add[q]);
                     }
                     long long lpos[kEdgeUnroll];
                     warp_append_multi<kEdgeUnroll>(fresh, P.capS, &sm.n_nxt, err, lpos);
@@ -458,6 +471,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 int v[kSettleUnroll];
                 bool ok[kSettleUnroll];
                 int a[kSettleUnroll], b[kSettleUnroll];
+                bool may[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
                     const int j = base + q * BLOCK + tid;
@@ -466,9 +480,10 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                 }
                 double x[kSettleUnroll];
                 int pos[kSettleUnroll], hs[kSettleUnroll];
+                unsigned code[kSettleUnroll];
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
-                    pos[q] = 0; x[q] = 0.0; hs[q] = -1;
+                    pos[q] = 0; x[q] = 0.0; hs[q] = -1; code[q] = 0u;
                     if (ok[q]) {
                         if (SHASH && v[q] < 0) {   // table resident: residue and key in shared memory
                             hs[q] = ~v[q];
@@ -478,9 +493,13 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                                 const unsigned bit = 1u << (v[q] & 31);
                                 if (!(atomicOr(&s_seen[v[q] >> 5], bit) & bit)) n_new++;
                             } else {
-                                v[q] = s_keys[hs[q]];
+                                const unsigned key = (unsigned)s_keys[hs[q]];
+                                v[q] = (int)(key & idmask);
+                                if (has_code) code[q] = key >> P.idbits;   // min(deg, cap): a lower bound of the degree
                             }
                         } else {
+                            if (has_code) code[q] = (unsigned)v[q] >> P.idbits;
+                            v[q] = (int)((unsigned)v[q] & idmask);
                             x[q] = T.take(v[q], epoch, pos[q]);
                         }
                     }
@@ -488,7 +507,9 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
                     a[q] = 0; b[q] = 0;
-                    if (ok[q] && will_push) { const int2 nr = __ldg(P.node_rec + v[q]); a[q] = nr.x; b[q] = nr.x + nr.y; }
+                    // necessary for graph.h:94: r >= rmax * code (code = 0 when unknown); the exact test on the fetched degree follows
+                    may[q] = ok[q] && will_push && x[q] >= P.rmax * (double)code[q];
+                    if (may[q]) { const int2 nr = __ldg(P.node_rec + v[q]); a[q] = nr.x; b[q] = nr.x + nr.y; }
                 }
                 // reserve[v] += coef * r (graph.h:90): logged by slot for table residents (summed after the last level),
                 // in the compact support arrays for slab residents
@@ -500,7 +521,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                     tbl[q] = SHASH && hs[q] >= 0;
                     first[q] = ok[q] && !tbl[q] && pos[q] < 0;
                     push[q] = false; st[q] = -1; dg[q] = 1; val[q] = x[q];
-                    if (ok[q] && will_push) {
+                    if (may[q]) {
                         const unsigned d = (unsigned)(b[q] - a[q]);
                         if (d == 0) push[q] = true;                                   // graph.h:91-93: back to the source
                         else if (x[q] >= P.rmax * (double)d) {                        // graph.h:94
@@ -645,8 +666,9 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             }
         }
         for (int j = tid; j < n_tslots; j += BLOCK) {
-            const int id = DENSE ? j : s_keys[j];
+            int id = DENSE ? j : s_keys[j];
             if (id == -1) continue;
+            id = (int)((unsigned)id & idmask);
             const double x = s_nxt_dyn[j];
             if (!DENSE) s_keys[j] = -1;
             s_nxt_dyn[j] = 0.0;   // the table is empty again for the next source
@@ -983,8 +1005,11 @@ int plan_cluster(gp_graph *g, long long S, int L, double rmax, int K, long long 
     cp->G = G; cp->clusters = clusters;
     cp->hub_min_deg = g_push_hub_deg > 0 ? g_push_hub_deg : 64 * G;
     cp->capP = capF;
-    // a level pushes at most capF edges; hashed ownership spreads them evenly over the G x G streams of a cluster
-    cp->capX = G == 1 ? 1 : std::min<long long>(capF, std::max<long long>(4096, 8 * capF / ((long long)G * G)));
+    // a level pushes at most min(nnz + n, 1/rmax) edges (every pushed edge carries >= rmax of a level's <= 1 total mass; a
+    // dangling node returns its residue over one pseudo-edge); hashed ownership spreads them evenly over the G x G streams
+    long long capE = g->nnz + n;
+    if (rmax > 0.0) capE = (long long)std::min<double>((double)capE, std::ceil(1.0 / rmax * 1.0001) + 16.0);
+    cp->capX = G == 1 ? 1 : std::min<long long>(capE, std::max<long long>(4096, 8 * capE / ((long long)G * G)));
     // a pushing node of degree d carries r >= rmax * d, and a level's residues sum to <= 1
     double hub = rmax > 0.0 ? std::ceil(1.0 / (rmax * cp->hub_min_deg)) + 16.0 : (double)n;
     cp->capHub = G == 1 ? 1 : (int)std::min<double>(hub, (double)std::min<long long>(n, 1ll << 24));
@@ -993,8 +1018,8 @@ int plan_cluster(gp_graph *g, long long S, int L, double rmax, int K, long long 
     cp->off_ps = o; o += align_up(ctas * cp->capP * 4, 256);
     cp->off_pl = o; o += align_up(ctas * cp->capP * 4, 256);
     cp->off_pa = o; o += align_up(ctas * cp->capP * 8, 256);
-    cp->off_xi = o; o += align_up(ctas * G * cp->capX * 4, 256);
-    cp->off_xv = o; o += align_up(ctas * G * cp->capX * 8, 256);
+    cp->off_xi = o; o += align_up(ctas * 2 * G * cp->capX * 4, 256);   // two generations (level parity)
+    cp->off_xv = o; o += align_up(ctas * 2 * G * cp->capX * 8, 256);
     cp->off_ci = o; o += align_up(ctas * K * 4, 256);
     cp->off_cv = o; o += align_up(ctas * K * 8, 256);
     cp->off_hs = o; o += align_up((size_t)clusters * cp->capHub * 4, 256);
@@ -1009,7 +1034,7 @@ int ensure_packed(gp_graph *g, cudaStream_t stream) {
     if (g->d_packed) return GP_OK;
     int idbits = 1;
     while (idbits < 32 && (1ll << idbits) < g->n) idbits++;
-    if (32 - idbits < 3) idbits = 32;   // fewer than 3 spare bits: no code, the node record is always fetched
+    if (31 - idbits < 3) idbits = 32;   // fewer than 3 spare bits below the sign bit: no code, the node record is always fetched
     cudaError_t e = cudaMalloc(&g->d_packed, sizeof(int) * (size_t)std::max<long long>(g->nnz, 1));
     if (e != cudaSuccess) { gp_set_error("cudaMalloc of the packed CSR failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return GP_ERR_NOMEM; }
     g->idbits = idbits;
@@ -1054,6 +1079,12 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     char *base = (char *)g->scratch;
     PushParams P{};
     P.indptr = g->d_indptr; P.node_rec = g->d_node_rec; P.indices = g->d_indices; P.n = (int)g->n;
+    P.packed = nullptr; P.idbits = 32;
+    if (pl.mode == GP_SCRATCH_HBM) {   // MODE 0 / 2 read the CSR copy with the degree codes
+        rc = ensure_packed(g, stream);
+        if (rc != GP_OK) return rc;
+        P.packed = g->d_packed; P.idbits = g->idbits;
+    }
     P.node_idx = d_node_idx; P.S = S; P.coef = g->d_coef; P.L = L; P.rmax = rmax; P.K = K;
     P.out_row = d_row; P.out_col = d_col; P.out_val = d_val; P.out_val32 = d_val32;
     P.tab = (Slot *)(base + pl.off_tab);

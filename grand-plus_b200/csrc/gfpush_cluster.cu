@@ -42,6 +42,10 @@ constexpr int kBuckets = kClusterSlots / 4;   // 4-key buckets: one 16-byte shar
 constexpr int kEmpty = -1;
 constexpr int kEdgeUnroll = 4;
 
+constexpr int kBigLen = 2048;    // entries longer than this are expanded by all warps of the CTA together
+constexpr int kBigCap = 32;
+constexpr int kItemBatch = 2;    // push-list entries a warp expands together
+constexpr int kChunk = 128;      // edges per push-list entry (longer entries are cut when they are appended)
 constexpr int kCandCap = 1024;   // nodes per level (and CTA) whose degree code allows a push; more are handled inline
 constexpr int kRankCap = 64;     // the radix select refines until the boundary bucket is this small, then rank-counts it
 
@@ -63,14 +67,22 @@ struct CSmem {
         } cand;
     };
     unsigned cnt[kClusterMaxG];      // entries this CTA appended to the stream of each destination (this level)
-    unsigned inbox[kClusterMaxG];    // entries every sender appended to MY stream (written by the senders before barrier #2)
+    unsigned inbox[2][kClusterMaxG];    // [level parity] entries every sender appended to MY stream (written by the senders before the barrier)
+    unsigned pushed[2][kClusterMaxG];   // [level parity] push-list entries every CTA expanded at this level
     unsigned pre[kClusterMaxG + 1];  // exchange / final select: prefix sums over the senders
+    long long seg_off[kClusterMaxG]; // exchange: element offset of every sender's stream to me, minus its prefix
     long long it;                    // (first CTA) the cluster's current source
     int n_push;                      // local push-list entries of this level
     int n_sel;                       // settle candidates
     int n_out, n_bucket, n_cand;
     int sel_bin, sel_above, sel_inbin;
     int seed_slot;
+    int next_item;                   // expand: next push-list entry to hand to a warp
+    int n_big;                       // expand: entries left for the all-warps pass
+    int big_st[kBigCap];
+    unsigned big_len[kBigCap];
+    double big_add[kBigCap];
+    int n_list;                      // top-k: reserves above the pre-filter threshold, compacted into add[] / start[]
     int full;                        // a probe sequence ran out: this source goes to the slab kernel, stop probing
     // cluster-wide state, valid in the first CTA's copy
     unsigned c_push[2];              // push-list entries of all CTAs, by level parity
@@ -188,6 +200,9 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
     constexpr int LOGG = Log2<G>::v;
     constexpr int kOwnerShift = G > 1 ? 32 - LOGG : 31;   // hash >> kOwnerShift = owning CTA (unused when G == 1)
     constexpr int kBucketShift = 32 - LOGG - 12;          // the 12 hash bits below the owner bits pick the bucket
+    // Long entries are shared by the whole cluster (a second cluster barrier per level) only when the cluster is large
+    // enough for one CTA's hub to matter; small clusters expand their own entries and pay one barrier per level.
+    constexpr bool kShareHubs = G >= 4;
     __shared__ CSmem sm;
     extern __shared__ double s_vals[];                      // [kClusterSlots] next-level residues
     int *s_keys = reinterpret_cast<int *>(s_vals + kClusterSlots);   // [kClusterSlots] packed node, kEmpty = free
@@ -211,20 +226,24 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
     int *hub_start = P.hub_start + cid * P.capHub;
     int *hub_deg = P.hub_deg + cid * P.capHub;
     double *hub_add = P.hub_add + cid * P.capHub;
-    int *x_id = P.x_id + cta * G * P.capX;       // my streams, one per destination
-    double *x_val = P.x_val + cta * G * P.capX;
+    // my streams, one per destination, in two generations (level parity): without a barrier between settle and expand
+    // a fast CTA already writes level l+1 while a slow one still reads level l
+    int *x_id_base = P.x_id + cta * 2 * G * P.capX;
+    double *x_val_base = P.x_val + cta * 2 * G * P.capX;
     unsigned long long *err = P.stats + 3;
 
     for (int i = tid; i < kClusterSlots; i += CB) { s_vals[i] = 0.0; s_keys[i] = kEmpty; }
     double rsv[SPT];                             // reserve of slot j * CB + tid
 #pragma unroll
     for (int j = 0; j < SPT; j++) rsv[j] = 0.0;
+    if (tid < kClusterMaxG) sm.cnt[tid] = 0;
     if (tid == 0) {
-        sm.c_push[0] = sm.c_push[1] = 0; sm.c_hub[0] = sm.c_hub[1] = 0; sm.c_flags = 0; sm.n_push = 0; sm.n_sel = 0; sm.full = 0;
+        sm.c_push[0] = sm.c_push[1] = 0; sm.c_hub[0] = sm.c_hub[1] = 0; sm.c_flags = 0; sm.n_push = 0; sm.n_sel = 0; sm.full = 0; sm.next_item = 0; sm.n_big = 0;
         for (int i = 0; i < 8; i++) sm.ph[i] = 0;
     }
-    unsigned long long st_edges = 0, st_sources = 0, st_cluster = 0, st_redo = 0;   // thread 0 only
-    unsigned st_frontier = 0, st_support = 0;                                         // every thread, reduced at the end
+    unsigned long long st_sources = 0, st_cluster = 0, st_redo = 0;   // thread 0 only
+    unsigned long long st_edges = 0;                                    // lane 0 of every warp
+    unsigned st_frontier = 0, st_support = 0;                           // every thread, reduced at the end
     const long long t_begin = clock64();
     if (tid == 0) sm.t_prev = t_begin;
 #define GPC_PHASE(i) do { if (tid == 0) { const long long t_now = clock64(); sm.ph[i] += t_now - sm.t_prev; sm.t_prev = t_now; } } while (0)
@@ -249,24 +268,31 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
         }
         const int2 src_rec = __ldg(P.node_rec + src);
         unsigned src_front = 0;                 // work counters of this source (dropped when it is handed over)
-        unsigned long long src_edges = 0;
+        unsigned long long src_edges = 0;       // (lane 0 of every warp counts the entries it expanded)
         int src_packed = src;
         if (has_code) {
-            const unsigned cap = (1u << (32 - P.idbits)) - 2u;
+            const unsigned cap = (1u << (31 - P.idbits)) - 1u;
             src_packed = (int)((unsigned)src | (min((unsigned)src_rec.y, cap) << P.idbits));
         }
         bool ovf = false;
         // A push-list entry {start, len, add}: the first CB of a level stay in the tile arrays of the expansion.
         auto add_entry = [&](int e_start, unsigned e_len, double e_add, int par) {
-            if (G > 1 && e_len >= (unsigned)P.hub_min_deg) {
+            if (kShareHubs && e_len >= (unsigned)P.hub_min_deg) {
                 const unsigned p = atomicAdd(&ldr->c_hub[par], 1u);
                 if (p < (unsigned)P.capHub) { hub_start[p] = e_start; hub_deg[p] = (int)e_len; hub_add[p] = e_add; }
                 else ovf = true;
             } else {
-                const int p = atomicAdd(&sm.n_push, 1);
-                if (p < CB) { sm.start[p] = e_start; sm.off[p] = e_len; sm.add[p] = e_add; }
-                else if (p < P.capP) { push_start[p] = e_start; push_len[p] = (int)e_len; push_add[p] = e_add; }
-                else ovf = true;
+                // entries are cut into chunks of kChunk edges -- the unit a warp expands in one go, so the level balances
+                // over the warps like an edge-parallel expansion without a search for the owner of an edge; entries
+                // beyond kBigLen stay whole and are expanded by all warps together
+                const unsigned step = e_len > (unsigned)kBigLen ? e_len : (unsigned)kChunk;
+                for (unsigned o = 0; o < e_len; o += step) {
+                    const int p = atomicAdd(&sm.n_push, 1);
+                    const unsigned l = min(step, e_len - o);
+                    if (p < CB) { sm.start[p] = e_start + (int)o; sm.off[p] = l; sm.add[p] = e_add; }
+                    else if (p < P.capP) { push_start[p] = e_start + (int)o; push_len[p] = (int)l; push_add[p] = e_add; }
+                    else ovf = true;
+                }
             }
         };
         // Exact push decision of a node whose degree code allows it (graph.h:91-95); fetches its {start, degree} record.
@@ -286,16 +312,21 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
         if (tid == 0) {
             if (rank == 0) { st_sources++; st_cluster++; }
             if (mine) sm.seed_slot = find_slot(s_keys, (hsrc >> kBucketShift) & (kBuckets - 1), src_packed, 1);   // empty table
-            int n0 = 0;
+            sm.n_push = 0;
             if (push0) {
                 if (deg0 == 0) {
-                    if (rank == 0) { sm.start[0] = -1; sm.off[0] = 1u; sm.add[0] = 1.0; n0 = 1; }
+                    if (rank == 0) { sm.start[0] = -1; sm.off[0] = 1u; sm.add[0] = 1.0; sm.n_push = 1; }
                 } else {
                     const unsigned lo = (unsigned)((unsigned long long)deg0 * rank / G), hi = (unsigned)((unsigned long long)deg0 * (rank + 1) / G);
-                    if (hi > lo) { sm.start[0] = src_rec.x + (int)lo; sm.off[0] = hi - lo; sm.add[0] = 1.0 / (double)deg0; n0 = 1; }
+                    const unsigned l0 = hi - lo;
+                    const unsigned step = l0 > (unsigned)kBigLen ? l0 : (unsigned)kChunk;
+                    int n0 = 0;
+                    for (unsigned o = 0; o < l0; o += step, n0++) {   // (at most kBigLen / kChunk chunks, all in the tile arrays)
+                        sm.start[n0] = src_rec.x + (int)(lo + o); sm.off[n0] = min(step, l0 - o); sm.add[n0] = 1.0 / (double)deg0;
+                    }
+                    sm.n_push = n0;
                 }
             }
-            sm.n_push = n0;
         }
         __syncthreads();
         if (mine) {
@@ -316,105 +347,188 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
             if (level == 0) {
                 if (!push0) break;
                 n_local = sm.n_push;
-            } else {
-                if (G > 1) {
-                    if (tid == 0 && sm.n_push) atomicAdd(&ldr->c_push[par], (unsigned)sm.n_push);
-                    csync();   // #1: every CTA's push list and the hub list of this level are complete
-                }
+            } else if (kShareHubs) {
+                if (tid == 0 && sm.n_push) atomicAdd(&ldr->c_push[par], (unsigned)sm.n_push);
+                csync();   // #1: every CTA's push list and the hub list of this level are complete
                 n_local = min((long long)sm.n_push, P.capP);
-                if (G > 1) n_hub = (int)min(ldr->c_hub[par], (unsigned)P.capHub);
-                const unsigned n_all = G > 1 ? ldr->c_push[par] + ldr->c_hub[par] : (unsigned)n_local;
-                if (n_all == 0) break;   // nothing pushes: every later residue is zero (the reserve is complete)
-                if (G > 1 && rank == 0 && tid == 0) { sm.c_push[par ^ 1] = 0; sm.c_hub[par ^ 1] = 0; }
+                n_hub = (int)min(ldr->c_hub[par], (unsigned)P.capHub);
+                if (ldr->c_push[par] + ldr->c_hub[par] == 0) break;   // nothing pushes: every later residue is zero
+                if (rank == 0 && tid == 0) { sm.c_push[par ^ 1] = 0; sm.c_hub[par ^ 1] = 0; }
+            } else {
+                n_local = min((long long)sm.n_push, P.capP);
+                if (G == 1 && n_local == 0) break;
             }
-            if (G > 1 && tid < G) sm.cnt[tid] = 0;
             // ---------------------------------------------------------------- expand (graph.h:94-100)
+            // One warp per push-list entry (entries are handed out through a shared counter): the lanes read consecutive
+            // CSR entries, so there is no search for the owner of an edge and no barrier inside the level.  Pushing nodes
+            // have tens to hundreds of neighbours on every BASELINE shape (a node only pushes while deg <= r / rmax);
+            // the rare long entry (a hub source's slice) is expanded by all warps together in a second pass.
+            // One edge per lane: the neighbour goes to the table (G == 1) or to its owner's stream (G > 1).
+            int *x_id = x_id_base + (long long)par * G * P.capX;
+            double *x_val = x_val_base + (long long)par * G * P.capX;
+            auto sink = [&](const int vp, const double av, const bool ok) {
+                if (G == 1) {
+                    if (ok && !*(volatile int *)&sm.full) {
+                        const int slot = find_slot(s_keys, (hash_node((unsigned)vp & idmask) >> kBucketShift) & (kBuckets - 1), vp, P.max_probe);
+                        if (slot >= 0) atomicAdd(s_vals + slot, av);   // graph.h:98
+                        else { ovf = true; sm.full = 1; }
+                    }
+                } else {
+                    const unsigned act = __ballot_sync(0xffffffffu, ok);
+                    if (ok) {
+                        const unsigned dst = hash_node((unsigned)vp & idmask) >> kOwnerShift;
+                        const unsigned peers = __match_any_sync(act, dst);
+                        const int leader = __ffs(peers) - 1;
+                        unsigned pos = 0;
+                        if (lane == leader) pos = atomicAdd(&sm.cnt[dst], (unsigned)__popc(peers));
+                        pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+                        if (pos < (unsigned)P.capX) {
+                            x_id[dst * P.capX + pos] = vp;
+                            x_val[dst * P.capX + pos] = av;
+                        } else ovf = true;
+                    }
+                }
+            };
             const int n_items = n_local + n_hub;
-            for (int base = 0; base < n_items; base += CB) {
-                const int j = base + tid;
-                unsigned len = 0;
-                int start = 0;
-                double add = 0.0;
-                if (j < n_local) {
-                    if (base == 0) { start = sm.start[tid]; len = sm.off[tid]; add = sm.add[tid]; }   // written by settle
-                    else { start = push_start[j]; len = (unsigned)push_len[j]; add = push_add[j]; }
-                } else if (j < n_items) {   // this CTA's slice of a hub entry
-                    const int h = j - n_local;
+            auto load_item = [&](const int i, int &st, unsigned &len, double &add) {
+                st = 0; len = 0; add = 0.0;
+                if (i < n_local) {
+                    if (i < CB) { st = sm.start[i]; len = sm.off[i]; add = sm.add[i]; }   // written by settle
+                    else { st = push_start[i]; len = (unsigned)push_len[i]; add = push_add[i]; }
+                } else if (i < n_items) {   // this CTA's slice of a hub entry
+                    const int h = i - n_local;
                     const unsigned d = (unsigned)__ldcg(hub_deg + h);
                     const unsigned lo = (unsigned)((unsigned long long)d * rank / G), hi = (unsigned)((unsigned long long)d * (rank + 1) / G);
-                    start = __ldcg(hub_start + h) + (int)lo; len = hi - lo; add = __ldcg(hub_add + h);
+                    st = __ldcg(hub_start + h) + (int)lo; len = hi - lo; add = __ldcg(hub_add + h);
                 }
-                unsigned total;
-                const unsigned excl = gp_block_exclusive_scan<CB>(len, sm.warp_scan, total);
-                sm.off[tid] = excl; sm.start[tid] = start; sm.add[tid] = add;
-                if (tid == 0) { sm.off[CB] = total; src_edges += total; }
-                __syncthreads();
-                for (unsigned e0 = (unsigned)(tid & ~31); e0 < total; e0 += CB * kEdgeUnroll) {
-                    int vp[kEdgeUnroll];
-                    double av[kEdgeUnroll];
-                    bool ok[kEdgeUnroll];
+            };
+            for (;;) {
+                // a warp takes kItemBatch entries at a time and has the first 64 edges of each in flight together: the
+                // entries of a level are short, so the level costs about one memory round trip, not one per entry
+                int i0 = 0;
+                if (lane == 0) i0 = atomicAdd(&sm.next_item, kItemBatch);
+                i0 = __shfl_sync(0xffffffffu, i0, 0);
+                if (i0 >= n_items) break;
+                int st[kItemBatch];
+                unsigned len[kItemBatch];
+                double add[kItemBatch];
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) {
-                        const unsigned e = e0 + q * CB + lane;
-                        ok[q] = e < total;
-                        vp[q] = src_packed; av[q] = 0.0;
-                        if (ok[q]) {
-                            const int t = owner_of_edge<CB>(sm.off, e);
-                            const int st = sm.start[t];
-                            av[q] = sm.add[t];
-                            if (st >= 0) vp[q] = __ldcs(P.packed + st + (e - sm.off[t]));   // graph.h:96-97
-                        }
-                    }
-                    if (G == 1) {
-                        int slot[kEdgeUnroll];
-#pragma unroll
-                        for (int q = 0; q < kEdgeUnroll; q++) {
-                            slot[q] = 0;
-                            if (ok[q] && !*(volatile int *)&sm.full) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> kBucketShift) & (kBuckets - 1), vp[q], P.max_probe);
-                        }
-#pragma unroll
-                        for (int q = 0; q < kEdgeUnroll; q++) {
-                            if (ok[q]) {
-                                if (slot[q] >= 0) atomicAdd(s_vals + slot[q], av[q]);   // graph.h:98
-                                else { ovf = true; sm.full = 1; }
+                for (int k = 0; k < kItemBatch; k++) {
+                    load_item(i0 + k, st[k], len[k], add[k]);
+                    if (lane == 0) src_edges += len[k];
+                    if (len[k] > (unsigned)kChunk) {   // an uncut entry or a hub slice: all warps expand it together after this pass
+                        int bpos = 0;
+                        if (lane == 0) bpos = atomicAdd(&sm.n_big, 1);
+                        bpos = __shfl_sync(0xffffffffu, bpos, 0);
+                        if (bpos < kBigCap) {
+                            if (lane == 0) { sm.big_st[bpos] = st[k]; sm.big_len[bpos] = len[k]; sm.big_add[bpos] = add[k]; }
+                        } else {   // (more long entries than the list holds: this warp expands it alone)
+                            for (unsigned base = 0; base < len[k]; base += 32) {
+                                const bool ok = base + lane < len[k];
+                                int v = src_packed;
+                                if (ok && st[k] >= 0) v = __ldcs(P.packed + st[k] + base + lane);
+                                sink(v, add[k], ok);
                             }
                         }
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < kEdgeUnroll; q++) {
-                            const unsigned act = __ballot_sync(0xffffffffu, ok[q]);
-                            if (ok[q]) {
-                                const unsigned dst = hash_node((unsigned)vp[q] & idmask) >> kOwnerShift;
-                                const unsigned peers = __match_any_sync(act, dst);
-                                const int leader = __ffs(peers) - 1;
-                                unsigned pos = 0;
-                                if (lane == leader) pos = atomicAdd(&sm.cnt[dst], (unsigned)__popc(peers));
-                                pos = __shfl_sync(peers, pos, leader) + __popc(peers & ((1u << lane) - 1u));
-                                if (pos < (unsigned)P.capX) {
-                                    x_id[dst * P.capX + pos] = vp[q];
-                                    x_val[dst * P.capX + pos] = av[q];
-                                } else ovf = true;
-                            }
-                        }
+                        len[k] = 0;
                     }
                 }
-                __syncthreads();
+                int vp[kItemBatch][kChunk / 32];
+#pragma unroll
+                for (int k = 0; k < kItemBatch; k++) {
+#pragma unroll
+                    for (int q = 0; q < kChunk / 32; q++) {
+                        vp[k][q] = src_packed;
+                        if (st[k] >= 0 && (unsigned)(32 * q + lane) < len[k]) vp[k][q] = __ldcs(P.packed + st[k] + 32 * q + lane);   // graph.h:96-97
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kItemBatch; k++) {
+#pragma unroll
+                    for (int q = 0; q < kChunk / 32; q++)
+                        if ((unsigned)(32 * q) < len[k]) sink(vp[k][q], add[k], (unsigned)(32 * q + lane) < len[k]);   // (warp-uniform condition)
+                }
             }
-            if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; }
+            __syncthreads();
+            {
+                const int n_big = min(sm.n_big, kBigCap);
+                for (int bi = 0; bi < n_big; bi++) {
+                    const int st = sm.big_st[bi];
+                    const unsigned len = sm.big_len[bi];
+                    const double add = sm.big_add[bi];
+                    for (unsigned base = (unsigned)(tid & ~31); base < len; base += CB * kEdgeUnroll) {
+                        int vp[kEdgeUnroll];
+                        bool ok[kEdgeUnroll];
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            const unsigned e = base + CB * q + lane;
+                            ok[q] = e < len;
+                            vp[q] = src_packed;
+                            if (ok[q] && st >= 0) vp[q] = __ldcs(P.packed + st + e);
+                        }
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++)
+                            if (base + CB * q < len) sink(vp[q], add, ok[q]);
+                    }
+                }
+                if (n_big) __syncthreads();
+            }
+            if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; }
             GPC_PHASE(1);
             if (G > 1) {
-                // tell every receiver how much I sent it, then barrier #2: every stream of this level is complete and visible
-                if (tid < G) cg::this_cluster().map_shared_rank(&sm, tid)->inbox[rank] = min(sm.cnt[tid], (unsigned)P.capX);
-                csync();
-                // ------------------------------------------------------------ exchange: accumulate what was sent to me
+                // One table update per lane: find-or-claim + fp64 add (graph.h:98).
+                auto accumulate = [&](const int vp, const double av, const bool ok) {
+                    if (ok && !*(volatile int *)&sm.full) {
+                        const int slot = find_slot(s_keys, (hash_node((unsigned)vp & idmask) >> kBucketShift) & (kBuckets - 1), vp, P.max_probe);
+                        if (slot >= 0) atomicAdd(s_vals + slot, av);
+                        else { ovf = true; sm.full = 1; }
+                    }
+                };
+                // Tell every receiver how much I sent it and ARRIVE at the cluster barrier (every stream of this level is
+                // then complete and visible); while the other CTAs get there, accumulate what I sent to myself.
+                const unsigned own = min(sm.cnt[rank], (unsigned)P.capX);
+                if (tid < G) {
+                    CSmem *peer = cg::this_cluster().map_shared_rank(&sm, tid);
+                    peer->inbox[par][rank] = (unsigned)tid == rank ? 0u : min(sm.cnt[tid], (unsigned)P.capX);
+                    peer->pushed[par][rank] = (unsigned)n_items;   // lets everyone see when no CTA pushed anything
+                }
+                cg::this_cluster().barrier_arrive();
+                {
+                    const int *oid = x_id + rank * P.capX;
+                    const double *oval = x_val + rank * P.capX;
+                    for (unsigned e0 = tid; e0 < own; e0 += CB * kEdgeUnroll) {
+                        int vp[kEdgeUnroll];
+                        double av[kEdgeUnroll];
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) {
+                            const unsigned e = e0 + q * CB;
+                            vp[q] = 0; av[q] = 0.0;
+                            if (e < own) { vp[q] = __ldcg(oid + e); av[q] = __ldcg(oval + e); }
+                        }
+#pragma unroll
+                        for (int q = 0; q < kEdgeUnroll; q++) accumulate(vp[q], av[q], e0 + q * CB < own);
+                    }
+                }
+                cg::this_cluster().barrier_wait();
+                if (tid < G) sm.cnt[tid] = 0;   // (barriers separate this from the next level's appends)
+                if (!kShareHubs) {
+                    unsigned any = 0;
+#pragma unroll
+                    for (int q = 0; q < G; q++) any |= sm.pushed[par][q];
+                    if (any == 0) break;   // nothing was pushed anywhere: every later residue is zero (the reserve is complete)
+                }
+                // ------------------------------------------------------------ exchange: accumulate what the others sent me
                 if (tid < 32) {
-                    unsigned v = tid < G ? sm.inbox[tid] : 0u, incl = v;
+                    unsigned v = tid < G ? sm.inbox[par][tid] : 0u, incl = v;
 #pragma unroll
                     for (int o = 1; o < kClusterMaxG; o <<= 1) {
                         const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
                         if (lane >= o) incl += y;
                     }
-                    if (tid < G) sm.pre[tid + 1] = incl;
+                    if (tid < G) {
+                        sm.pre[tid + 1] = incl;
+                        sm.seg_off[tid] = (((cta0 + tid) * 2 + par) * G + rank) * P.capX - (long long)(incl - v);   // stream of sender tid, minus its prefix
+                    }
                     if (tid == 0) sm.pre[0] = 0;
                 }
                 __syncthreads();
@@ -422,34 +536,21 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                 for (unsigned e0 = tid; e0 < total; e0 += CB * kEdgeUnroll) {
                     int vp[kEdgeUnroll];
                     double av[kEdgeUnroll];
-                    bool ok[kEdgeUnroll];
 #pragma unroll
                     for (int q = 0; q < kEdgeUnroll; q++) {
                         const unsigned e = e0 + q * CB;
-                        ok[q] = e < total;
                         vp[q] = 0; av[q] = 0.0;
-                        if (ok[q]) {
-                            int s = 0;
+                        if (e < total) {
+                            int sdr = 0;
 #pragma unroll
-                            for (int k = 1; k < G; k++) s += e >= sm.pre[k];
-                            const long long a = ((cta0 + s) * G + rank) * P.capX + (e - sm.pre[s]);
+                            for (int k = 1; k < G; k++) sdr += e >= sm.pre[k];
+                            const long long a = sm.seg_off[sdr] + e;
                             vp[q] = __ldcg(P.x_id + a);
                             av[q] = __ldcg(P.x_val + a);
                         }
                     }
-                    int slot[kEdgeUnroll];
 #pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) {
-                        slot[q] = 0;
-                        if (ok[q] && !*(volatile int *)&sm.full) slot[q] = find_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> kBucketShift) & (kBuckets - 1), vp[q], P.max_probe);
-                    }
-#pragma unroll
-                    for (int q = 0; q < kEdgeUnroll; q++) {
-                        if (ok[q]) {
-                            if (slot[q] >= 0) atomicAdd(s_vals + slot[q], av[q]);   // graph.h:98
-                            else { ovf = true; sm.full = 1; }
-                        }
-                    }
+                    for (int q = 0; q < kEdgeUnroll; q++) accumulate(vp[q], av[q], e0 + q * CB < total);
                 }
                 GPC_PHASE(3);
             }
@@ -460,32 +561,30 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                 const int npar = nl & 1;
                 const bool will_push = nl < P.L - 1;
                 const double c = P.coef[nl];
+                // credit every slot: reserve += coef * r (graph.h:90 / :106) -- an untouched slot adds an exact zero, so the
+                // pass has no branch; the bits of `nz` remember which of my slots held a residue
+                unsigned nz = 0;
 #pragma unroll
-                for (int jb = 0; jb < SPT; jb += 8) {
-                    double r8[8];
-#pragma unroll
-                    for (int u = 0; u < 8; u++) r8[u] = s_vals[(jb + u) * CB + tid];
-                    long long any = 0;
-#pragma unroll
-                    for (int u = 0; u < 8; u++) any |= __double_as_longlong(r8[u]);
-                    if (any == 0) continue;   // residues are sums of positive pushes: eight +0.0
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const double r = r8[u];
-                        if (r != 0.0) {
-                            const int slot = (jb + u) * CB + tid;
-                            s_vals[slot] = 0.0;
-                            rsv[jb + u] += c * r;                              // graph.h:90 / :106
-                            src_front++;
-                            if (will_push) {
-                                const unsigned key = (unsigned)s_keys[slot];
-                                const unsigned code = has_code ? key >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
-                                if (r >= P.rmax * (double)code) {              // necessary for graph.h:94; the exact test follows
-                                    const int p = atomicAdd(&sm.n_sel, 1);
-                                    if (p < kCandCap) { sm.cand.key[p] = key; sm.cand.r[p] = r; }
-                                    else consider(key, r, npar);
-                                }
-                            }
+                for (int j = 0; j < SPT; j++) {
+                    const double r = s_vals[j * CB + tid];
+                    rsv[j] = fma(c, r, rsv[j]);
+                    if (__double2hiint(r) | __double2loint(r)) nz |= 1u << j;
+                    if (!will_push && r != 0.0) s_vals[j * CB + tid] = 0.0;
+                }
+                src_front += __popc(nz);
+                if (will_push) {
+                    // take the residues; a node whose degree code allows it becomes a candidate for the next push list
+                    while (nz) {
+                        const int slot = (__ffs(nz) - 1) * CB + tid;
+                        nz &= nz - 1;
+                        const double r = s_vals[slot];
+                        s_vals[slot] = 0.0;
+                        const unsigned key = (unsigned)s_keys[slot];
+                        const unsigned code = has_code ? key >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
+                        if (r >= P.rmax * (double)code) {                        // necessary for graph.h:94; the exact test follows
+                            const int p = atomicAdd(&sm.n_sel, 1);
+                            if (p < kCandCap) { sm.cand.key[p] = key; sm.cand.r[p] = r; }
+                            else consider(key, r, npar);
                         }
                     }
                 }
@@ -504,50 +603,71 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
         csync();   // #C: every CTA's overflow flag has landed
         const bool redo = ldr->c_flags != 0;
         if (!redo) { st_frontier += src_front; st_edges += src_edges; }
-        // Pre-filter for the select: every lane's largest (K <= 32) or second largest (K <= 64) reserve is at least the
-        // warp's minimum of them, so at least K reserves of this CTA are >= tau and nothing below tau can be among its K
-        // largest.  The bulk of a source's support (thousands of reserves of a few 1e-7) then never reaches the
-        // histogram, whose few exponent bins would otherwise serialise the shared-memory atomics.
+        // Pre-filter: v_r = the r-th largest (distinct) of a warp's 32 lane maxima, r = ceil(K / warps): every warp holds
+        // at least r reserves >= its v_r, so at least K reserves of this CTA are >= tau = min over the warps, and nothing
+        // below tau can be among its K largest.  The bulk of a source's support (thousands of reserves of a few 1e-7)
+        // never reaches the select; the few dozen survivors are compacted into shared memory and rank-counted.
         double tau = 0.0;
-        if (!redo && P.K <= 64) {
-            double m1 = 0.0, m2 = 0.0;
+        const int per_warp = (P.K + CB / 32 - 1) / (CB / 32);
+        if (!redo && per_warp <= 8) {
+            long long m1 = 0;   // positive doubles order like their bit patterns
+#pragma unroll
+            for (int j = 0; j < SPT; j++) m1 = max(m1, __double_as_longlong(rsv[j]));
+            long long v = 0x7fffffffffffffffll;
+            for (int t = 0; t < per_warp; t++) {   // next distinct lane maximum below v
+                long long w = m1 < v ? m1 : 0;
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+                v = w;
+            }
+            if (lane == 0) sm.wtau[tid >> 5] = __longlong_as_double(v);
+            __syncthreads();
+            tau = sm.wtau[0];
+            for (int i = 1; i < CB / 32; i++) tau = fmin(tau, sm.wtau[i]);
+        }
+        if (tid == 0) sm.n_list = 0;
+        __syncthreads();
+        bool listed = !redo && tau > 0.0;
+        if (listed) {
 #pragma unroll
             for (int j = 0; j < SPT; j++) {
-                const double x = rsv[j];
-                m2 = fmax(m2, fmin(m1, x));
-                m1 = fmax(m1, x);
+                if (rsv[j] >= tau) {
+                    const int pos = atomicAdd(&sm.n_list, 1);
+                    if (pos < CB) { sm.add[pos] = rsv[j]; sm.start[pos] = (int)((unsigned)s_keys[j * CB + tid] & idmask); }
+                }
             }
-            double w = P.K <= 32 ? m1 : m2;
-#pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) w = fmin(w, __shfl_xor_sync(0xffffffffu, w, o));
-            if (lane == 0) sm.wtau[tid >> 5] = w;
             __syncthreads();
-            for (int i = 0; i < CB / 32; i++) tau = fmax(tau, sm.wtau[i]);
+            listed = sm.n_list <= CB;   // (uniform) more than the list holds: select from the registers instead
         }
+        const int n_list = listed ? sm.n_list : 0;
+        auto each_list = [&](auto f) {
+            for (int i = tid; i < n_list; i += CB) f(sm.add[i], sm.start[i]);
+        };
         auto each_reg = [&](auto f) {
 #pragma unroll
             for (int j = 0; j < SPT; j++)
-                if (rsv[j] > 0.0 && rsv[j] >= tau) f(rsv[j], (int)((unsigned)s_keys[j * CB + tid] & idmask));
+                if (rsv[j] > 0.0) f(rsv[j], (int)((unsigned)s_keys[j * CB + tid] & idmask));
         };
         if (!redo) {
+            auto emit_out = [&](int pos, int id, double v) {
+                const long long o = it * P.K + pos;
+                P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
+                if (P.out_val32) P.out_val32[o] = (float)v;
+            };
+            int *cand_id = P.cand_id + cta * P.K;
+            double *cand_val = P.cand_val + cta * P.K;
+            auto emit_cand = [&](int pos, int id, double v) { cand_id[pos] = id; cand_val[pos] = v; };
+            int n;
+            if (G == 1) n = listed ? block_topk(sm, P.K, n_list <= kBucketCap, each_list, emit_out) : block_topk(sm, P.K, false, each_reg, emit_out);
+            else n = listed ? block_topk(sm, P.K, n_list <= kBucketCap, each_list, emit_cand) : block_topk(sm, P.K, false, each_reg, emit_cand);
             if (G == 1) {
-                const int n = block_topk(sm, P.K, false, each_reg, [&](int pos, int id, double v) {
-                    const long long o = it * P.K + pos;
-                    P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
-                    if (P.out_val32) P.out_val32[o] = (float)v;
-                });
                 // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
                 for (int i = n + tid; i < P.K; i += CB) {
                     const long long o = it * P.K + i;
                     P.out_row[o] = 0; P.out_col[o] = 0; P.out_val[o] = 0.0;
                     if (P.out_val32) P.out_val32[o] = 0.f;
                 }
-            } else {
-                int *cand_id = P.cand_id + cta * P.K;
-                double *cand_val = P.cand_val + cta * P.K;
-                const int n = block_topk(sm, P.K, false, each_reg, [&](int pos, int id, double v) { cand_id[pos] = id; cand_val[pos] = v; });
-                if (tid == 0) sm.n_cand = n;
-            }
+            } else if (tid == 0) sm.n_cand = n;
         }
         // the table is empty again for the next source
 #pragma unroll
@@ -607,14 +727,13 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
     st_frontier = __reduce_add_sync(0xffffffffu, st_frontier);
     st_support = __reduce_add_sync(0xffffffffu, st_support);
     if (lane == 0) {
+        if (st_edges) { atomicAdd(P.stats + 0, st_edges); atomicAdd(P.cum + 0, st_edges); }
         if (st_frontier) { atomicAdd(P.stats + 1, (unsigned long long)st_frontier); atomicAdd(P.cum + 1, (unsigned long long)st_frontier); }
         if (st_support) { atomicAdd(P.stats + 2, (unsigned long long)st_support); atomicAdd(P.cum + 2, (unsigned long long)st_support); }
     }
     if (tid == 0) {
         sm.ph[7] = clock64() - t_begin;
         for (int i = 0; i < 8; i++) atomicAdd(P.phase + i, (unsigned long long)sm.ph[i]);
-        atomicAdd(P.stats + 0, st_edges);
-        atomicAdd(P.cum + 0, st_edges);
         atomicAdd(P.cum + 3, st_sources);
         atomicAdd(P.cum + 4, st_cluster);
         atomicAdd(P.cum + 5, st_redo);
@@ -624,7 +743,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
 #undef GPC_PHASE
 
 __global__ void pack_indices_kernel(const int2 *node_rec, const int *indices, long long nnz, int idbits, int *packed) {
-    const unsigned cap = (1u << (32 - idbits)) - 2u;
+    const unsigned cap = (1u << (31 - idbits)) - 1u;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) {
         const unsigned v = (unsigned)indices[i];

@@ -12,7 +12,7 @@ struct ClusterPushParams {
     const int2 *node_rec;      // [n] {indptr[v], degree}
     const int *packed;         // [nnz] neighbour id | min(degree, cap) << idbits  (gpc_pack_indices)
     int n;
-    int idbits;                // ids occupy the low idbits bits of a packed entry; 32 = no degree code
+    int idbits;                // ids occupy the low idbits bits of a packed entry, the code the bits up to 30; 32 = no degree code
     const int *node_idx;
     long long S;
     const double *coef;        // device [L]
@@ -28,8 +28,8 @@ struct ClusterPushParams {
     int *push_len;             // [ctas][capP]
     double *push_add;          // [ctas][capP]  r / deg
     long long capP;
-    int *x_id;                 // [ctas][G][capX]  exchange streams sender -> owner: packed node
-    double *x_val;             // [ctas][G][capX]  ... and the pushed amount
+    int *x_id;                 // [ctas][2][G][capX]  exchange streams sender -> owner (two generations): packed node
+    double *x_val;             // [ctas][2][G][capX]  ... and the pushed amount
     long long capX;
     int *cand_id;              // [ctas][K]  local top-k candidates
     double *cand_val;          // [ctas][K]
@@ -48,7 +48,7 @@ struct ClusterPushParams {
     unsigned long long *redo_count;
 };
 
-// packed[e] = indices[e] | min(deg(indices[e]), cap) << idbits, cap = 2^(32-idbits) - 2
+// packed[e] = indices[e] | min(deg(indices[e]), cap) << idbits, cap = 2^(31-idbits) - 1 (packed entries are non-negative)
 int gpc_pack_indices(const int2 *node_rec, const int *indices, long long nnz, int idbits, int *packed, int num_sms,
                      cudaStream_t stream);
 // dynamic shared memory one CTA needs

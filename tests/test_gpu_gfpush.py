@@ -234,8 +234,8 @@ TIERS = {
     "cluster_g8": dict(push_cluster=8),
     "cluster_g16": dict(push_cluster=16),
     "cluster_g4_hubs": dict(push_cluster=4, push_hub_deg=8),
-    "cluster_g1_redo": dict(push_cluster=-1, push_cluster_probe=1),
-    "cluster_g2_redo": dict(push_cluster=2, push_cluster_probe=1),
+    "cluster_g1_redo": dict(push_cluster=-1, push_cluster_probe=3),
+    "cluster_g2_redo": dict(push_cluster=2, push_cluster_probe=2),
     "cluster_g4_few": dict(push_cluster=4, push_max_clusters=3),
 }
 
@@ -268,10 +268,12 @@ def test_gfpush_tiers_give_the_oracle_rows_and_counters(tier):
         assert st["cluster_sources"] == 0 and st["redo_sources"] == 0
     else:
         assert st["cluster_sources"] + st["redo_sources"] == len(src)
-        if "redo" in tier:
+        if tier == "cluster_g1_redo":   # one CTA's table at a probe limit of 3 buckets: (nearly) every source is handed over
+            assert 0 < st["redo_sources"] <= len(src), st
+        elif "redo" in tier:
             assert 0 < st["redo_sources"] < len(src), st
         elif tier == "cluster_g1":   # mean support 13.7 K: a few sources outgrow one CTA's 16 384 slots
-            assert st["redo_sources"] <= 0.1 * len(src), st
+            assert st["redo_sources"] <= 0.25 * len(src), st
         else:
             assert st["redo_sources"] == 0, st
     assert st2["sources"] == 2 * len(src)

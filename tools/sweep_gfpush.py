@@ -67,13 +67,14 @@ def main():
         ls = graph.last_stats()
         print(f"{name} S={S} {cfg:44s} rows/s={S * steps / t:12.0f}  edges/s={st['edges_pushed'] / t / 1e9:7.2f}G  "
               f"G={ls['cluster_size']} ctas={ls['ctas']} cluster={st['cluster_sources']} redo={st['redo_sources']} "
-              f"sup/src={st['support_total'] / max(st['sources'], 1):.0f} scratch={ls['scratch_bytes'] / 1e6:.0f}MB", flush=True)
+              f"sup/src={st['support_total'] / max(st['sources'], 1):.0f} scratch={ls['scratch_bytes'] / 1e6:.0f}MB "
+              f"[E={st['edges_pushed']} F={st['frontier_total']} S={st['support_total']}]", flush=True)
         ph = graph.phase_cycles(reset=True)
         if ph["resident"]:
             # CTA time per source: resident cycles of all CTAs / sources (a cluster of G CTAs spends G x its latency)
             us = ph["resident"] / 1965.0 / max(st["sources"], 1)
             print(f"    {us:.0f} us of CTA time per source; % by phase: " +
-                  " ".join(f"{n}={100.0 * v / ph['resident']:.1f}" for n, v in ph.items() if n != "resident"), flush=True)
+                  " ".join(f"{n}={100.0 * v / ph['resident']:.1f}" for n, v in ph.items() if n not in ("resident", "wide_expand", "wide_settle")), flush=True)
     for k, v in DEFAULTS.items():
         _lib.set_tuning(k, v)
 
