@@ -41,8 +41,10 @@
 int g_push_smem_hash = 1;     // "push_smem_hash": shared-memory residue table in front of the slabs (HBM mode, MODE 2 kernel):
                               // 0 off, 1 auto (on when the expected support is of the order of the table), 2 always on
 int g_push_smem_probe = 2;    // "push_smem_probe": 4-key buckets tried before a node is sent to the slab
-int g_push_cluster = 1;       // "push_cluster": the cluster kernel (gfpush_cluster.cu) for graphs beyond the dense shared-memory mode:
-                              // 0 off, 1 auto (cluster size from the expected support), 2/4/8/16 = that cluster size, -1 = one CTA
+int g_push_cluster = 0;       // "push_cluster": the cluster kernel (gfpush_cluster.cu) for graphs beyond the dense shared-memory mode:
+                              // 0 off (default: measured slower than the per-CTA kernels on every BASELINE shape,
+                              // profiles/r02_gfpush.md), 1 auto (cluster size from the expected support), 2/4/8/16 = that
+                              // cluster size, -1 = one CTA per source
 int g_push_cluster_probe = 128;   // "push_cluster_probe": 4-key buckets tried before a source is handed to the slab kernel
                                   // (at the loads the planner aims at the longest probe sequence is a few buckets)
 int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree are expanded by the whole cluster (0 = 64 x G)
@@ -116,6 +118,7 @@ struct PushSmem {
     int start[BLOCK];
     double val[BLOCK];
     unsigned warp_scan[BLOCK / 32 + 1];
+    double wtau[BLOCK / 32];   // top-k pre-filter: per-warp lower bounds of the K-th largest reserve
     union {
         unsigned hist[kHistBins];   // top-k: radix histogram
         int fl[kHistBins];          // levels: the first kSmallList entries of the frontier list (dead before the top-k)
@@ -124,6 +127,7 @@ struct PushSmem {
     int bid[kBucketCap];
     long long it;
     int n_push, n_nxt, n_sup, n_out, n_bucket;
+    int n_list;    // top-k: reserves above the pre-filter threshold, compacted into val[] / start[]
     int n_log;     // MODE 2: entries in the reserve log
     int n_tab;     // MODE 2: distinct nodes in the shared-memory table after the merge
     int table_on;  // MODE 2: this CTA currently uses the table (off when most edges spill: supports far beyond it)
@@ -601,15 +605,83 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             st_support += sup_all; st_maxsup = max(st_maxsup, sup_all);
         }
         const int n_tslots = merged ? P.hslots : 0;
-        // pass 0: exponent histogram of the compact reserve values (coalesced; no table access)
-        for (int j = tid; j < n_sup; j += BLOCK) {
-            const double x = sup_val[j];
-            if (x > 0.0) atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u);
+        // Pass A -- a threshold below which nothing can be among the K largest: v_r = the r-th largest (distinct) of a
+        // warp's 32 lane maxima, r = ceil(K / warps); every warp holds at least r reserves >= its v_r, so at least K
+        // reserves are >= tau = min over the warps.  Reads are batched four to a thread (the support of an Amazon2M-shape
+        // source is 152 K values in HBM: one load in flight per thread made every pass ~150 dependent round trips).
+        double tau = 0.0;
+        {
+            const int per_warp = (P.K + BLOCK / 32 - 1) / (BLOCK / 32);
+            if (per_warp <= 8) {
+                long long m1 = 0;   // non-negative doubles order like their bit patterns
+                for (int j0 = tid; j0 < n_sup; j0 += 4 * BLOCK) {
+                    long long x[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) x[q] = j0 + q * BLOCK < n_sup ? __double_as_longlong(sup_val[j0 + q * BLOCK]) : 0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) m1 = max(m1, x[q]);
+                }
+                for (int j = tid; j < n_tslots; j += BLOCK) m1 = max(m1, __double_as_longlong(s_nxt_dyn[j]));
+                long long v = 0x7fffffffffffffffll;
+                for (int t = 0; t < per_warp; t++) {   // next distinct lane maximum below v
+                    long long w = m1 < v ? m1 : 0;
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) w = max(w, __shfl_xor_sync(0xffffffffu, w, o));
+                    v = w;
+                }
+                if (lane == 0) sm.wtau[tid >> 5] = __longlong_as_double(v);
+                __syncthreads();
+                tau = sm.wtau[0];
+                for (int i = 1; i < BLOCK / 32; i++) tau = fmin(tau, sm.wtau[i]);
+            }
         }
-        for (int j = tid; j < n_tslots; j += BLOCK) {
-            const double x = s_nxt_dyn[j];
-            if (x > 0.0) atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u);
+        // Pass B -- the survivors (a few dozen) are compacted into shared memory (the tile arrays of the expansion are
+        // free now); the table is emptied for the next source on the way.  Every later pass of the select reads the list.
+        if (tid == 0) sm.n_list = 0;
+        __syncthreads();
+        const bool filtered = tau > 0.0;
+        auto keep = [&](double x, int id) {
+            const int pos = atomicAdd(&sm.n_list, 1);
+            if (pos < BLOCK) { sm.val[pos] = x; sm.start[pos] = id; }
+        };
+        if (filtered) {
+            for (int j0 = tid; j0 < n_sup; j0 += 4 * BLOCK) {
+                double x[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) x[q] = j0 + q * BLOCK < n_sup ? sup_val[j0 + q * BLOCK] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (x[q] >= tau) keep(x[q], sup_id[j0 + q * BLOCK]);
+            }
         }
+        int n_list = 0;
+        bool listed = false;
+        if (filtered) {
+            for (int j = tid; j < n_tslots; j += BLOCK) {
+                const double x = s_nxt_dyn[j];
+                if (x >= tau) keep(x, DENSE ? j : (int)((unsigned)s_keys[j] & idmask));
+            }
+            __syncthreads();
+            n_list = sm.n_list;
+            listed = n_list <= BLOCK;   // (uniform) more survivors than the list holds: select over the full arrays
+        }
+        // each(f): f(value > 0, node) for the calling thread's share of the values the select runs over
+        auto each = [&](auto f) {
+            if (listed) {
+                for (int i = tid; i < n_list; i += BLOCK) f(sm.val[i], sm.start[i]);
+            } else {
+                for (int j = tid; j < n_sup; j += BLOCK) {
+                    const double x = sup_val[j];
+                    if (x > 0.0) f(x, sup_id[j]);
+                }
+                for (int j = tid; j < n_tslots; j += BLOCK) {
+                    const double x = s_nxt_dyn[j];
+                    if (x > 0.0) f(x, DENSE ? j : (int)((unsigned)s_keys[j] & idmask));
+                }
+            }
+        };
+        // radix select (11-bit digits, exponent first) down to a boundary bucket of <= kBucketCap, then rank counting
+        each([&](double x, int) { atomicAdd(&sm.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u); });
         __syncthreads();
         int shift = 52, bits = 11;
         unsigned long long prefix = 0;  // value of key >> (shift+bits) shared by the boundary bucket
@@ -632,59 +704,31 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             __syncthreads();
             const int nshift = shift >= 11 ? shift - 11 : 0;
             const int nbits = shift >= 11 ? 11 : shift;
-            for (int j = tid; j < n_sup; j += BLOCK) {
-                const double x = sup_val[j];
-                if (x > 0.0) {
-                    const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-                    if ((key >> shift) == prefix)
-                        atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
-                }
-            }
-            for (int j = tid; j < n_tslots; j += BLOCK) {
-                const double x = s_nxt_dyn[j];
-                if (x > 0.0) {
-                    const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-                    if ((key >> shift) == prefix)
-                        atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
-                }
-            }
+            each([&](double x, int) {
+                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+                if ((key >> shift) == prefix) atomicAdd(&sm.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
+            });
             shift = nshift; bits = nbits;
             __syncthreads();
         }
         // final pass: everything above the boundary bucket is selected; the bucket goes to smem
-        for (int j = tid; j < n_sup; j += BLOCK) {
-            const double x = sup_val[j];
-            if (x > 0.0) {
-                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-                const unsigned long long t = key >> shift;
-                if (t > Tkey) {
-                    emit(P, it, src, atomicAdd(&sm.n_out, 1), sup_id[j], x);
-                } else if (t == Tkey) {
-                    const int pos = atomicAdd(&sm.n_bucket, 1);
-                    if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = sup_id[j]; }
-                }
+        each([&](double x, int id) {
+            const unsigned long long key = (unsigned long long)__double_as_longlong(x);
+            const unsigned long long t = key >> shift;
+            if (t > Tkey) {
+                emit(P, it, src, atomicAdd(&sm.n_out, 1), id, x);
+            } else if (t == Tkey) {
+                const int pos = atomicAdd(&sm.n_bucket, 1);
+                if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = id; }
             }
-        }
+        });
+        __syncthreads();
+        // the table is empty again for the next source
         for (int j = tid; j < n_tslots; j += BLOCK) {
-            int id = DENSE ? j : s_keys[j];
-            if (id == -1) continue;
-            id = (int)((unsigned)id & idmask);
-            const double x = s_nxt_dyn[j];
             if (!DENSE) s_keys[j] = -1;
-            s_nxt_dyn[j] = 0.0;   // the table is empty again for the next source
-            if (x > 0.0) {
-                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-                const unsigned long long t = key >> shift;
-                if (t > Tkey) {
-                    emit(P, it, src, atomicAdd(&sm.n_out, 1), id, x);
-                } else if (t == Tkey) {
-                    const int pos = atomicAdd(&sm.n_bucket, 1);
-                    if (pos < kBucketCap) { sm.bkey[pos] = key; sm.bid[pos] = id; }
-                }
-            }
+            s_nxt_dyn[j] = 0.0;
         }
         if (DENSE && merged) for (int i = tid; i < (P.hslots + 31) / 32; i += BLOCK) s_seen[i] = 0u;
-        __syncthreads();
         {
             // rank-count the boundary bucket: keep its `want_bucket` largest (ties: lower slot first)
             const int nb = min(sm.n_bucket, kBucketCap);
@@ -1149,6 +1193,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     g->last.ctas = cp.G > 0 ? (long long)cp.clusters * cp.G : std::min<long long>(pl.ctas, S);
     g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->cscratch_bytes);
     g->last.scratch_mode = pl.mode; g->last.kernel_launches = launches; g->last.cluster_size = cp.G;
+    g->last.table_slots = cp.G > 0 ? kClusterSlots : pl.hslots;
     return GP_OK;
 }
 

@@ -108,7 +108,7 @@ typedef struct {
     int64_t cluster_sources; /* cumulative stats only: sources finished by the cluster kernel          */
     int64_t redo_sources;    /* cumulative stats only: sources it handed over to the slab kernel       */
     int32_t cluster_size;    /* CTAs per source of the cluster kernel (0 = per-CTA kernels only)       */
-    int32_t reserved;
+    int32_t table_slots;     /* shared-memory residue-table slots per CTA (0 = residues on the HBM slabs)  */
 } gp_push_stats;
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out);
 /* Counters summed over every gfpush since creation / the last reset (device-wide synchronise);

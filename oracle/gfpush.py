@@ -167,13 +167,18 @@ def load_reference():
     return mod
 
 
-def reference_gfpush(indptr, indices, node_idx, coef, rmax, K):
+def reference_gfpush(indptr, indices, node_idx, coef, rmax, K, nthreads=None):
     """Run the reference exactly as /root/reference/model.py:249-268 does.
-    Returns (row_idx, col_idx, value) as the reference filled them."""
+    Returns (row_idx, col_idx, value) as the reference filled them.
+    ``nthreads``: the reference's constructor calls omp_set_num_threads(40) (graph.h:41,46); when given, the same
+    call is made again with this value before gfpush_omp -- the unmodified binary with NUMTHREAD = nthreads
+    (BASELINE.md 3 asks for the cpu_count setting beside the literal 40)."""
     prop = load_reference()
     indptr = np.array(indptr, dtype=np.int32)
     indices = np.array(indices, dtype=np.int32)
     graph = prop.Graph(indptr, indices, 0)
+    if nthreads:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(nthreads))
     node_idx = np.ascontiguousarray(node_idx, dtype=np.int32)
     S = node_idx.shape[0]
     row = np.zeros(S * K, dtype=np.int32)

@@ -22,7 +22,7 @@ SHAPES = {
 }
 TIER_TUNING = {"cluster": dict(push_cluster=1), "table": dict(push_cluster=0, push_smem_hash=2),
                "slabs": dict(push_cluster=0, push_smem_hash=0)}
-TUNING_DEFAULTS = dict(push_cluster=1, push_smem_hash=1)
+TUNING_DEFAULTS = dict(push_cluster=0, push_smem_hash=1)
 
 
 def _build(shape):
