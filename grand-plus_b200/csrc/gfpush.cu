@@ -32,7 +32,9 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -936,12 +938,17 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, bool redo_only, Plan
         return o;
     };
     size_t budget = (size_t)g->cfg.max_scratch_bytes;
-    if (budget == 0) {
-        size_t free_b = 0, total_b = 0;
-        GP_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        budget = (free_b + g->scratch_bytes) / 2;
-    }
     Plan tmp{};
+    if (budget == 0) {
+        // cudaMemGetInfo takes the driver's allocation lock (0.2 - 6 ms per call measured inside a running pipeline): only
+        // ask when the scratch the handle already holds does not cover this call
+        if (g->scratch && bytes_for(ctas, &tmp) <= g->scratch_bytes) budget = g->scratch_bytes;
+        else {
+            size_t free_b = 0, total_b = 0;
+            GP_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            budget = (free_b + g->scratch_bytes) / 2;
+        }
+    }
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
     pl->block = block; pl->mode = mode; pl->ctas = ctas; pl->capF = capF; pl->capS = capS;
     pl->hslots = hslots; pl->capLog = capLog;
@@ -1358,13 +1365,29 @@ int gp_gfpush(gp_graph *g, const int32_t *node_idx, int64_t S, const double *coe
     double *d_val = (double *)g->d_out;
     int *d_row = (int *)((char *)g->d_out + slots * 8);
     int *d_col = d_row + slots;
+    // GP_TRACE=1: host wall time of every stage of the host-buffer entry point (diagnostics for end-to-end numbers)
+    static const bool trace = getenv("GP_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
     GP_CUDA_TRY(cudaMemcpyAsync(g->d_node, node_idx, sizeof(int) * (size_t)S, cudaMemcpyHostToDevice, g->stream));
     int rc = push_device_locked(g, g->d_node, S, coef, L, rmax, K, d_row, d_col, d_val, nullptr, g->stream);
     if (rc != GP_OK) return rc;
+    const auto t1 = now();
+    if (trace) GP_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    const auto t2 = now();
     GP_CUDA_TRY(cudaMemcpyAsync(value, d_val, slots * 8, cudaMemcpyDeviceToHost, g->stream));
     GP_CUDA_TRY(cudaMemcpyAsync(row_idx, d_row, slots * 4, cudaMemcpyDeviceToHost, g->stream));
     GP_CUDA_TRY(cudaMemcpyAsync(col_idx, d_col, slots * 4, cudaMemcpyDeviceToHost, g->stream));
-    return collect_stats(g, g->stream);
+    if (trace) GP_CUDA_TRY(cudaStreamSynchronize(g->stream));
+    const auto t3 = now();
+    rc = collect_stats(g, g->stream);
+    if (trace)
+        fprintf(stderr, "[gp_gfpush] S=%lld K=%d: enqueue %.3f ms, kernels %.3f ms, D2H of %.1f MB %.3f ms, flags %.3f ms\n",
+                (long long)S, K, ms(t0, t1), ms(t1, t2), (double)slots * 16 / 1e6, ms(t2, t3), ms(t3, now()));
+    return rc;
 }
 
 int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset) {

@@ -67,10 +67,27 @@ def test_emb_matches_reference_golden():
         _assert_close(out.cpu().numpy(), want64, sc)
 
 
+# kernel variants reachable through gp_set_tuning: the default (register-staged, 64-bit loads), 128-bit loads, and the
+# TMA-staged cp.async.bulk kernel with two buffer depths -- every one must give the oracle's rows
+AGG_VARIANTS = {"default": {}, "vec4": {"agg_max_vec": 4}, "vec1": {"agg_max_vec": 1}, "bulk": {"agg_kernel": 2},
+                "bulk_nbuf2": {"agg_kernel": 2, "agg_nbuf": 2}, "chunk1": {"agg_max_chunk": 1}}
+AGG_DEFAULTS = {"agg_kernel": 0, "agg_nbuf": 0, "agg_max_vec": 2, "agg_max_chunk": 4, "agg_smem_kb": 96}
+
+
+@pytest.fixture(params=sorted(AGG_VARIANTS))
+def agg_variant(request):
+    from grandplus_b200 import _lib
+    for k, v in AGG_VARIANTS[request.param].items():
+        _lib.set_tuning(k, v)
+    yield request.param
+    for k, v in AGG_DEFAULTS.items():
+        _lib.set_tuning(k, v)
+
+
 @pytest.mark.parametrize("Fdim", [1, 7, 64, 100, 500, 602, 1433, 2050])
 @pytest.mark.parametrize("n_aug", [1, 2])
-def test_fused_gather_matches_oracle(Fdim, n_aug):
-    """random_prop_fused == oracle(random_prop(features[nbr], ...)) for every vector width / tiling."""
+def test_fused_gather_matches_oracle(Fdim, n_aug, agg_variant):
+    """random_prop_fused == oracle(random_prop(features[nbr], ...)) for every vector width / tiling / kernel variant."""
     import torch
     from grandplus_b200 import model as gm
     rng = np.random.default_rng(Fdim * 10 + n_aug)
