@@ -89,6 +89,16 @@ SIGNATURES = {
     "gp_segments_from_sorted_index": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "gp_narrow_index": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "gp_set_tuning": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int64]),
+    "gp_emb_dropout_fwd": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, c_vp, c_vp, c_vp, ctypes.c_int64,
+                                          ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_float, c_vp, ctypes.c_int64,
+                                          c_vp, c_vp]),
+    "gp_emb_dropout_bwd": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, ctypes.c_int64,
+                                          ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, c_vp, ctypes.c_int64, c_vp]),
+    "gp_emb_dropout_mask": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64,
+                                           c_vp, c_vp]),
+    "gp_lazy_adam_rows": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.c_int32, c_vp, ctypes.c_int64, c_vp,
+                                         ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_float, c_vp]),
     "gp_dropnode_mask": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64,
                                         ctypes.c_uint64, c_vp, c_vp]),
 }

@@ -263,25 +263,96 @@ def random_prop_fused(features: DeviceFeatures, neighbor_idx, mat_scores, mat_id
     return _finish(out, m, n_aug, return_mask)
 
 
-def emb(weight, attr_idx, node_idx, attr_data, input_droprate=0.0, training=False):
-    """model_mag.py:48-55 with the embedding table resident on the GPU (the reference keeps it on the
-    CPU and copies the gathered rows every batch, model_mag.py:49).  Differentiable w.r.t. ``weight``."""
+class _EmbFn(torch.autograd.Function):
+    """MLP.emb (model_mag.py:48-55): out[n,:] = sum_a w_a drop(E[idx_a,:]) / (sum_a w_a + 1e-10), gradient w.r.t. the
+    embedding table only.  ``sparse_grad``: the gradient is a coalesced sparse COO tensor over the rows the batch touched
+    (what :class:`grandplus_b200.optim.SparseRowAdam` consumes) instead of a dense [n_rows, H] tensor."""
+
+    @staticmethod
+    def forward(ctx, weight, nbr, row_ptr, score, B, p, seed, offset, sparse_grad):
+        lib = _lib.load()
+        dev = weight.device
+        H = int(weight.shape[1])
+        needs_grad = weight.requires_grad
+        if p > 0.0:
+            ld_out = (H + 3) // 4 * 4
+            out = torch.empty((B, ld_out), dtype=torch.float32, device=dev)
+            denom = torch.empty((B,), dtype=torch.float32, device=dev)
+            _lib.check(lib.gp_emb_dropout_fwd(_vp(weight), int(weight.shape[0]), int(weight.stride(0)), H, _vp(row_ptr), _vp(nbr),
+                                              _vp(score), int(B), float(p), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
+                                              EPS_EMB, _vp(out), ld_out, _vp(denom), _stream(dev)))
+            out = out if ld_out == H else out[:, :H]
+        else:
+            o3, _, denom = _launch_fwd(weight, H, weight.stride(0), row_ptr, None, 0, nbr, score, B, int(score.numel()), 0.0,
+                                       False, 1, 0, 0, None, False, EPS_EMB, needs_grad)
+            out = o3[0]
+            denom = None if denom is None else denom[0]
+        if needs_grad:
+            ctx.save_for_backward(nbr, row_ptr, score, denom)
+            ctx.meta = (tuple(weight.shape), H, int(B), float(p), int(seed), int(offset), bool(sparse_grad))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        nbr, row_ptr, score, denom = ctx.saved_tensors
+        shape, H, B, p, seed, offset, sparse_grad = ctx.meta
+        lib = _lib.load()
+        dev = grad_out.device
+        grad_out = grad_out.contiguous()
+        if sparse_grad:
+            rows, slot = torch.unique(nbr, return_inverse=True)     # the distinct table rows of the batch, ascending
+            slot = slot.to(torch.int32).contiguous()
+            target = torch.zeros((int(rows.numel()), H), dtype=torch.float32, device=dev)
+        else:
+            rows, slot = None, nbr
+            target = torch.zeros(shape, dtype=torch.float32, device=dev)
+        if p > 0.0:
+            _lib.check(lib.gp_emb_dropout_bwd(_vp(grad_out), int(grad_out.stride(0)), H, _vp(row_ptr), _vp(slot), _vp(score),
+                                              _vp(denom), B, p, seed & (2**64 - 1), offset & (2**64 - 1), _vp(target),
+                                              int(target.stride(0)), _stream(dev)))
+        else:
+            a = _lib.AggregateBwdArgs()
+            a.grad_out = grad_out.data_ptr(); a.ld_grad_out = int(grad_out.stride(0)); a.denom = denom.data_ptr()
+            a.row_ptr = row_ptr.data_ptr(); a.nbr = slot.data_ptr(); a.score = score.data_ptr()
+            a.B = B; a.n_entries = int(score.numel()); a.F = H; a.p = 0.0; a.training = 0; a.n_aug = 1; a.mask_in = 0
+            a.grad_table = target.data_ptr(); a.ld_grad_table = int(target.stride(0)); a.n_table_rows = int(target.shape[0])
+            _lib.check(lib.gp_aggregate_bwd(ctypes.byref(a), _stream(dev)))
+        if sparse_grad:
+            grad = torch.sparse_coo_tensor(rows.to(torch.int64)[None, :], target, size=shape, is_coalesced=True,
+                                           check_invariants=False)
+        else:
+            grad = target
+        return (grad,) + (None,) * 8
+
+
+def emb(weight, attr_idx, node_idx, attr_data, input_droprate=0.0, training=False, sparse_grad=False, seed=None,
+        offset=None):
+    """model_mag.py:48-55 with the embedding table resident on the GPU (the reference keeps it on the CPU and copies the
+    gathered rows every batch, model_mag.py:49).  Differentiable w.r.t. ``weight``.  A non-zero ``input_droprate`` in
+    training mode is the element-wise dropout of model_mag.py:50, drawn from counter-based Philox inside the fused
+    kernel (forward and backward regenerate the same mask from (seed, offset); :func:`emb_dropout_mask` exports it).
+    ``sparse_grad=True`` keeps the gradient on the touched rows."""
     _need_cuda(weight, node_idx, attr_data)
     dev = weight.device
     attr_idx = attr_idx.to(dev)
     score = attr_data.to(torch.float32).contiguous()
     row_ptr, B = segments_from_sorted_index(node_idx)
-    if training and input_droprate > 0.0:
-        # element-wise input dropout on the gathered rows (model_mag.py:50): gather + dropout are
-        # library ops here, the segmented reduction still runs in the fused kernel
-        rows = F.dropout(weight[attr_idx], input_droprate, training=True)
-        out, _ = _AggregateFn.apply(rows, int(rows.shape[1]), row_ptr, None, score, B, 0.0, False, 1, 0, 0, None,
-                                    EPS_EMB, False)
-        return out[0]
     nbr = narrow_index(attr_idx, int(weight.shape[0]))
     w = weight if weight.stride(-1) == 1 else weight.contiguous()
-    out, _ = _AggregateFn.apply(w, int(w.shape[1]), row_ptr, nbr, score, B, 0.0, False, 1, 0, 0, None, EPS_EMB, False)
-    return out[0]
+    p = float(input_droprate) if training else 0.0
+    if p > 0.0 and (seed is None or offset is None):
+        st = _seed_state()
+        seed, offset = st.seed, st.next()
+    return _EmbFn.apply(w, nbr, row_ptr, score, B, p, seed or 0, offset or 0, bool(sparse_grad))
+
+
+def emb_dropout_mask(nza: int, H: int, p: float, seed: int, offset: int, device) -> torch.Tensor:
+    """The element keep-mask :func:`emb` draws for (seed, offset): uint8 [nza, H]."""
+    lib = _lib.load()
+    mask = torch.empty((nza, H), dtype=torch.uint8, device=device)
+    _lib.check(lib.gp_emb_dropout_mask(int(nza), int(H), float(p), int(seed) & (2**64 - 1), int(offset) & (2**64 - 1),
+                                       _vp(mask), _stream(mask.device)))
+    return mask
 
 
 def aggregate_slots(features: DeviceFeatures, col, val32, slot_rows=None, dropnode_rate=0.5, training=True,

@@ -117,8 +117,8 @@ int gp_gfpush_cumulative_stats(gp_graph *g, gp_push_stats *out, int reset);
 
 /* Profiling hook (the reference only takes an unused gettimeofday pair, graph.h:54-56,129-130): SM cycles the
  * persistent CTAs spent per phase, summed over CTAs since the last reset:
- * [0] fetch + level 0, [1] expand (gfpush_kernel) / table growth (hash tier), [2] settle / expand,
- * [3] reserve merge / settle, [4] top-k, [5] expand of each source's widest level, [6] its settle, [7] kernel residency.
+ * [0] fetch + level 0, [1] expand, [2] settle, [3] reserve merge (per-CTA kernels) / exchange (cluster kernel), [4] top-k,
+ * [5] expand of each source's widest level, [6] its settle (per-CTA kernels), [7] kernel residency.
  * Device-wide synchronise. */
 int gp_gfpush_phase_cycles(gp_graph *g, uint64_t out[8], int reset);
 
@@ -186,6 +186,32 @@ typedef struct {
 } gp_aggregate_bwd_args;
 int gp_aggregate_bwd(const gp_aggregate_bwd_args *args, void *stream);
 
+/* MLP.emb with a non-zero input dropout (model_mag.py:48-55; scripts/run_mag.sh uses 0.0, which is gp_aggregate_fwd with
+ * eps 1e-10): out[b,:] = sum_j w_j * drop(table[idx_j,:]) / (sum_j w_j + eps), drop(x) = keep ? x/(1-p) : 0 per ELEMENT,
+ * keep drawn from Philox4x32-10 at counter (entry j, column block) keyed by (seed, offset).  row_ptr int32[B+1] segments
+ * the entries by output row (node_idx ascending, dim_size = node_idx[-1]+1); denom_out (nullable) receives sum_j w_j + eps.
+ * The backward regenerates the same mask and accumulates into COMPACT gradient rows: slot[j] is the position of entry j's
+ * table row among the batch's distinct rows, grad_rows is [n_distinct, H] (zeroed by the caller). */
+int gp_emb_dropout_fwd(const float *table, int64_t n_table_rows, int64_t ld_table, int32_t H, const int32_t *row_ptr,
+                       const int32_t *idx, const float *weight, int64_t B, double p, uint64_t seed, uint64_t offset,
+                       float eps, float *out, int64_t ld_out, float *denom_out, void *stream);
+int gp_emb_dropout_bwd(const float *grad_out, int64_t ld_grad_out, int32_t H, const int32_t *row_ptr, const int32_t *slot,
+                       const float *weight, const float *denom, int64_t B, double p, uint64_t seed, uint64_t offset,
+                       float *grad_rows, int64_t ld_grad_rows, void *stream);
+/* The element mask the two calls above draw, uint8 [nza, H] (for export / tests). */
+int gp_emb_dropout_mask(int64_t nza, int32_t H, double p, uint64_t seed, uint64_t offset, uint8_t *d_mask, void *stream);
+
+/* Optimizer step of the embedding table on the touched rows only, EXACTLY equal to the reference's dense
+ * torch.optim.Adam(lr, betas, eps, weight_decay=0) over the whole table (model_mag.py:312-313,369): a row that is not touched
+ * still moves under dense Adam while its moments decay, so every row remembers the step it was last brought up to date
+ * (last_step int32[n_rows]) and the skipped zero-gradient steps last_step+1 .. upto are replayed when it is next read or
+ * updated.  rows int64[R] (distinct; NULL = all rows 0..R-1).  grad_rows == NULL: catch up to step `upto` only (call before
+ * a forward pass that reads the rows, and with rows == NULL before inference / saving).  grad_rows != NULL ([R, H]):
+ * catch up to `upto`, then apply step upto+1 with the gradient. */
+int gp_lazy_adam_rows(float *param, float *exp_avg, float *exp_avg_sq, int32_t *last_step, int64_t ld, int32_t H,
+                      const int64_t *rows, int64_t R, const float *grad_rows, int64_t ld_grad, int32_t upto, float lr,
+                      float beta1, float beta2, float eps, void *stream);
+
 /* mat_idx (int64, ascending; model.py:84 takes dim_size = mat_idx[-1]+1) -> CSR row_ptr int32[B+1].
  * *d_flags (int32[2], device) receives {1 if unsorted or out of range, 0 otherwise; unused}. */
 int gp_segments_from_sorted_index(const int64_t *d_idx, int64_t n, int64_t B, int32_t *d_row_ptr,
@@ -200,12 +226,12 @@ int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, 
 /* Performance knobs for sweeps (profiles/); defaults are the measured best and results never depend on them.
  * Aggregation: "agg_kernel" (0 auto, 1 register-staged LDG kernel, 2 TMA-staged cp.async.bulk kernel), "agg_nbuf",
  * "agg_max_vec", "agg_max_chunk", "agg_smem_kb".
- * GFPush (HBM mode): "push_smem_hash" (shared-memory residue table in front of the slabs: 0 off, 1 auto from rmax,
- * 2 always), "push_smem_probe" (4-key buckets tried before a node goes to the slab), "push_max_ctas" (cap on persistent CTAs, for
- * scaling experiments); the opt-in L2-resident cluster tier: "push_hash" (1 = on), "push_cluster" (CTAs per source:
- * 0 auto, 1, 2, 4, 8, 16), "push_hash_slots", "push_hash_block", "push_l2_mb", "push_load_pct", "push_list_div",
- * "push_pilot", "push_max_clusters".  The same keys are read from the GP_TUNING environment variable
- * ("key=value,key=value") by the Python loader. */
+ * GFPush (graphs beyond the dense shared-memory mode): "push_smem_hash" (shared-memory residue table in front of the slabs:
+ * 0 off, 1 auto from rmax, 2 always), "push_smem_probe" (4-key buckets tried before a node goes to the slab), "push_max_ctas"
+ * (cap on persistent CTAs, for scaling experiments); the opt-in cluster kernel (one source per thread-block cluster):
+ * "push_cluster" (0 off, 1 auto, -1 = one CTA, 2, 4, 8, 16 CTAs per source), "push_cluster_probe", "push_hub_deg",
+ * "push_max_clusters".  The same keys are read from the GP_TUNING environment variable ("key=value,key=value") by the
+ * Python loader. */
 int gp_set_tuning(const char *key, int64_t value);
 
 #ifdef __cplusplus

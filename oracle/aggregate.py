@@ -99,12 +99,15 @@ def random_prop_backward_feats(grad_out, scores, idx, p, training, mask=None):
     return (m / den[idx, 0])[:, None] * np.asarray(grad_out, dtype=np.float64)[idx]
 
 
-def emb_backward_table(grad_node, n_attr, attr_idx, node_idx, attr_data):
-    """d out / d table for MLP.emb (eval-mode dropout): dense [n_attr,H] fp64 gradient."""
+def emb_backward_table(grad_node, n_attr, attr_idx, node_idx, attr_data, elem_mask=None, input_droprate=0.0):
+    """d out / d table for MLP.emb: dense [n_attr,H] fp64 gradient (elem_mask [nza,H]: the input-dropout mask of
+    model_mag.py:50 in training mode, through which the gradient flows scaled by 1/(1-p))."""
     node_idx = np.asarray(node_idx, dtype=np.int64)
     w = np.asarray(attr_data, dtype=np.float64)
     den = _segment_sum(w[:, None], node_idx, int(node_idx[-1]) + 1, np.float64) + 1e-10
     contrib = (w / den[node_idx, 0])[:, None] * np.asarray(grad_node, dtype=np.float64)[node_idx]
+    if elem_mask is not None and input_droprate > 0.0:
+        contrib = contrib * (np.asarray(elem_mask, dtype=np.float64) / (1.0 - input_droprate))
     out = np.zeros((n_attr, contrib.shape[1]), dtype=np.float64)
     np.add.at(out, np.asarray(attr_idx, dtype=np.int64), contrib)
     return out

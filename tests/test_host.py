@@ -129,6 +129,14 @@ assert gcol.shape == (S, K) and torch.equal(gcol.reshape(-1), torch.arange(S * K
 assert torch.equal(gval, gcol.to(torch.float64) * 0.5)
 t = gd.max_over_ranks(1.0 + rank)
 assert t == 2.0
+# row-sparse gradient all-reduce (SURVEY 8e, MAG backward): ranks touch overlapping rows, ragged counts
+rows = torch.tensor([2, 5, 9], dtype=torch.int64) if rank == 0 else torch.tensor([5, 7], dtype=torch.int64)
+vals = torch.arange(rows.numel() * 3, dtype=torch.float32).reshape(-1, 3) + 10 * rank
+ur, uv = gd.allreduce_sparse_rows(rows, vals)
+assert ur.tolist() == [2, 5, 7, 9]
+want = {2: [0., 1., 2.], 5: [3. + 10., 4. + 11., 5. + 12.], 7: [13., 14., 15.], 9: [6., 7., 8.]}
+for r, v in zip(ur.tolist(), uv.tolist()):
+    assert v == want[r], (r, v)
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 '''
