@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             const int next_level = level + 1;
             const bool will_push = next_level < P.L - 1;
             const double c = P.coef[next_level];
+            const long long log_base = sm.n_log;   // (SHASH) this level's slice of the reserve log starts here
             if (tid == 0) { st_frontier += n_nxt; sm.n_push = 0; }
             __syncthreads();
             int n_new = 0;   // MODE 1: nodes reached for the first time
@@ -535,12 +536,21 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
                         }
                     }
                 }
+                // The reserve log is written at the frontier-list position (nearly every frontier node is a table resident, so
+                // compacting the log would cost a ballot round per batch for nothing): entry log_base + j, -1 = not a resident.
                 long long ps[kSettleUnroll], pp[kSettleUnroll], pl[kSettleUnroll];
-                if (SHASH) warp_append_multi<kSettleUnroll>(tbl, P.capLog, &sm.n_log, err, pl);
+                if (SHASH) {
+#pragma unroll
+                    for (int q = 0; q < kSettleUnroll; q++) {
+                        pl[q] = ok[q] ? log_base + base + q * BLOCK + tid : -1;
+                        if (pl[q] >= P.capLog) { pl[q] = -1; atomicOr(err, kErrOverflow); }
+                    }
+                }
                 warp_append_multi<kSettleUnroll>(first, P.capS, &sm.n_sup, err, ps);
                 warp_append_multi<kSettleUnroll>(push, P.capF, &sm.n_push, err, pp);
 #pragma unroll
                 for (int q = 0; q < kSettleUnroll; q++) {
+                    if (SHASH && !tbl[q] && pl[q] >= 0) log_id[pl[q]] = -1;
                     if (tbl[q]) {
                         if (pl[q] >= 0) { log_id[pl[q]] = hs[q]; log_val[pl[q]] = c * x[q]; }
                     } else if (first[q]) {
@@ -563,6 +573,7 @@ __global__ void __launch_bounds__(BLOCK, 1024 / BLOCK) gfpush_kernel(PushParams 
             __syncthreads();
             if (tid == 0) {
                 sm.n_nxt = 0;
+                if (SHASH) sm.n_log += n_nxt;
                 if (lvl_E >= sm.wide_E) { sm.wide_E = lvl_E; sm.wide_expand = t_e; sm.wide_settle = clock64() - sm.t_prev; }
             }
             GP_PHASE(2);
@@ -922,8 +933,8 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, bool redo_only, Plan
         }
     }
     // reserve log of MODE 2: at most one entry per table slot per level
-    // (a level logs at most min(slots, capF) entries)
-    const long long capLog = hslots ? std::min((long long)std::max(L, 1) * hslots, 1 + (long long)std::max(L - 1, 0) * capF) + 8192 : 0;
+    // (one entry per frontier node and level, at the node's frontier-list position)
+    const long long capLog = hslots ? 1 + (long long)std::max(L - 1, 0) * capF + 8192 : 0;
     auto bytes_for = [&](long long c, Plan *p) {
         size_t o = 0;
         p->off_tab = o; o += align_up((size_t)c * n * (mode == GP_SCRATCH_HBM ? 16 : 0), 256);
