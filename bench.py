@@ -398,7 +398,7 @@ def measure_strong(name, dev, rank, world, total_sources, steps=3):
             dist.barrier()
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         e[0].record()
-        col, val, val32, (lo, hi) = gd.gfpush_sharded(graph, src, coef, w["rmax"], w["K"], gather=False)
+        col, val, val32, (lo, hi) = gd.gfpush_sharded(graph, src, coef, w["rmax"], w["K"], gather=False, check=False)
         e[1].record()
         if world > 1:
             col, val, val32 = gd.all_gather_rows([col, val, val32], S)

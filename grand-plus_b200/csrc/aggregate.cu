@@ -89,116 +89,148 @@ __device__ __forceinline__ void row_range(const AggParams &P, long long b, long 
     }
 }
 
-// Weight of entry jj in augmentation a (0 when dropped / pad / out of range).
-__device__ __forceinline__ float entry_weight(const AggParams &P, long long jj, int a, float s, bool &keep) {
-    keep = true;
-    if (P.use_mask) {
-        if (P.mask_in) keep = P.mask_in[(long long)a * P.n_entries + jj] != 0;
-        else keep = !P.drop_all && gp_dropnode_keep((unsigned long long)jj, (unsigned)a, P.seed, P.offset, P.thresh);
-        return keep ? s * P.scale : 0.0f;
+// Keep bits of entry jj for all augmentations (bit a = kept in augmentation a): read from the caller's mask or drawn
+// from ONE Philox block per entry.
+__device__ __forceinline__ unsigned entry_keep_bits(const AggParams &P, long long jj, int n_aug) {
+    if (!P.use_mask) return 0xFu;
+    if (P.mask_in) {
+        unsigned bits = 0;
+        for (int a = 0; a < n_aug; a++) bits |= (P.mask_in[(long long)a * P.n_entries + jj] != 0 ? 1u : 0u) << a;
+        return bits;
     }
+    return P.drop_all ? 0u : gp_dropnode_keep4((unsigned long long)jj, P.seed, P.offset, P.thresh);
+}
+// Weight of entry jj in augmentation a (0 when dropped / pad / out of range).
+__device__ __forceinline__ float entry_weight(const AggParams &P, unsigned bits, int a, float s, bool &keep) {
+    keep = (bits >> a) & 1u;
+    if (P.use_mask) return keep ? s * P.scale : 0.0f;
     return s;
 }
 
 template <int VEC, int NCHUNK, int NAUG, int UNROLL>
 __global__ void __launch_bounds__(kAggBlock) aggregate_fwd_kernel(AggParams P) {
     const int lane = gp_lane();
-    const long long warp = ((long long)blockIdx.x * kAggBlock + threadIdx.x) >> 5;
-    const long long b = warp / P.n_ctile;
-    if (b >= P.B) return;  // warp-uniform
-    const int ctile = (int)(warp - b * P.n_ctile);
-    const int col0 = ctile * P.tile_cols + lane * VEC;  // this lane's first column in chunk 0
+    // Persistent warps: warp w takes (row, column tile) items w, w + W, ... and loads the entry metadata (neighbour id,
+    // score) of its NEXT item before it gathers the rows of the current one, so the metadata round trip of an item is
+    // hidden behind the row traffic of the previous item instead of sitting in front of its own.
+    const long long n_items = P.B * P.n_ctile;
+    const long long n_warps = ((long long)gridDim.x * kAggBlock) >> 5;
+    long long item = ((long long)blockIdx.x * kAggBlock + threadIdx.x) >> 5;
+    if (item >= n_items) return;  // warp-uniform
 
-    long long j0, j1;
-    row_range(P, b, j0, j1);
-
-    float acc[NAUG][NCHUNK][VEC];
-    float wsum[NAUG];
-#pragma unroll
-    for (int a = 0; a < NAUG; a++) {
-        wsum[a] = 0.0f;
-#pragma unroll
-        for (int c = 0; c < NCHUNK; c++)
-#pragma unroll
-            for (int k = 0; k < VEC; k++) acc[a][c][k] = 0.0f;
-    }
-
-    for (long long j = j0; j < j1; j += 32) {
-        const long long jj = j + lane;
-        const bool valid = jj < j1;
-        int my_nbr = 0;
-        float my_m[NAUG];
-        bool any = false;
-        {
-            float s = 0.0f;
-            if (valid) {
-                s = P.score[jj];
-                my_nbr = P.nbr ? P.nbr[jj] : (int)jj;
-            }
-            const bool live = valid && (P.row_ptr != nullptr || s > 0.0f);  // slot layout: skip zero pads
-#pragma unroll
-            for (int a = 0; a < NAUG; a++) {
-                bool keep = false;
-                my_m[a] = live ? entry_weight(P, jj, a, s, keep) : 0.0f;
-                if (valid && P.mask_out && ctile == 0) P.mask_out[(long long)a * P.n_entries + jj] = (live && keep) ? 1 : 0;
-                any |= (my_m[a] != 0.0f);
-            }
+    // metadata of the first 32-entry block of an item: entry range, this lane's neighbour id and score
+    long long nj0 = 0, nj1 = 0;
+    int n_nbr = 0;
+    float n_s = 0.0f;
+    auto fetch = [&](long long it) {
+        row_range(P, it / P.n_ctile, nj0, nj1);
+        const long long jj = nj0 + lane;
+        n_nbr = 0; n_s = 0.0f;
+        if (jj < nj1) {
+            n_s = P.score[jj];
+            n_nbr = P.nbr ? P.nbr[jj] : (int)jj;
         }
-        unsigned kept = __ballot_sync(0xffffffffu, any);  // entries some augmentation keeps
-        while (kept) {
-            int src_lane[UNROLL];
-            int nb[UNROLL];
-            int cnt = 0;
+    };
+    fetch(item);
+    for (; item < n_items; item += n_warps) {
+        const long long b = item / P.n_ctile;
+        const int ctile = (int)(item - b * P.n_ctile);
+        const int col0 = ctile * P.tile_cols + lane * VEC;  // this lane's first column in chunk 0
+        const long long j0 = nj0, j1 = nj1;
+        int first_nbr = n_nbr;
+        float first_s = n_s;
+        if (item + n_warps < n_items) fetch(item + n_warps);   // in flight while this item's rows stream
+
+        float acc[NAUG][NCHUNK][VEC];
+        float wsum[NAUG];
 #pragma unroll
-            for (int q = 0; q < UNROLL; q++) {
-                src_lane[q] = 0;
-                if (kept) { src_lane[q] = __ffs(kept) - 1; kept &= kept - 1; cnt = q + 1; }
-                nb[q] = __shfl_sync(0xffffffffu, my_nbr, src_lane[q]);
+        for (int a = 0; a < NAUG; a++) {
+            wsum[a] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < NCHUNK; c++)
+#pragma unroll
+                for (int k = 0; k < VEC; k++) acc[a][c][k] = 0.0f;
+        }
+
+        for (long long j = j0; j < j1; j += 32) {
+            const long long jj = j + lane;
+            const bool valid = jj < j1;
+            int my_nbr = 0;
+            float my_m[NAUG];
+            bool any = false;
+            {
+                float s = 0.0f;
+                if (j == j0) { s = first_s; my_nbr = first_nbr; }
+                else if (valid) {
+                    s = P.score[jj];
+                    my_nbr = P.nbr ? P.nbr[jj] : (int)jj;
+                }
+                const bool live = valid && (P.row_ptr != nullptr || s > 0.0f);  // slot layout: skip zero pads
+                const unsigned keep_bits = live ? entry_keep_bits(P, jj, NAUG) : 0u;   // one Philox block for all augmentations
+#pragma unroll
+                for (int a = 0; a < NAUG; a++) {
+                    bool keep = false;
+                    my_m[a] = live ? entry_weight(P, keep_bits, a, s, keep) : 0.0f;
+                    if (valid && P.mask_out && ctile == 0) P.mask_out[(long long)a * P.n_entries + jj] = (live && keep) ? 1 : 0;
+                    any |= (my_m[a] != 0.0f);
+                }
             }
-            float x[UNROLL][NCHUNK][VEC];
+            unsigned kept = __ballot_sync(0xffffffffu, any);  // entries some augmentation keeps
+            while (kept) {
+                int src_lane[UNROLL];
+                int nb[UNROLL];
+                int cnt = 0;
 #pragma unroll
-            for (int q = 0; q < UNROLL; q++) {
-                const float *row = P.table + (long long)nb[q] * P.ld_table;
+                for (int q = 0; q < UNROLL; q++) {
+                    src_lane[q] = 0;
+                    if (kept) { src_lane[q] = __ffs(kept) - 1; kept &= kept - 1; cnt = q + 1; }
+                    nb[q] = __shfl_sync(0xffffffffu, my_nbr, src_lane[q]);
+                }
+                float x[UNROLL][NCHUNK][VEC];
 #pragma unroll
-                for (int c = 0; c < NCHUNK; c++) {
-                    const int col = col0 + c * 32 * VEC;
-                    if (q < cnt && col < P.F) vec_load<VEC>(x[q][c], row + col);
-                    else {
+                for (int q = 0; q < UNROLL; q++) {
+                    const float *row = P.table + (long long)nb[q] * P.ld_table;
 #pragma unroll
-                        for (int k = 0; k < VEC; k++) x[q][c][k] = 0.0f;
+                    for (int c = 0; c < NCHUNK; c++) {
+                        const int col = col0 + c * 32 * VEC;
+                        if (q < cnt && col < P.F) vec_load<VEC>(x[q][c], row + col);
+                        else {
+#pragma unroll
+                            for (int k = 0; k < VEC; k++) x[q][c][k] = 0.0f;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < UNROLL; q++) {
+#pragma unroll
+                    for (int a = 0; a < NAUG; a++) {
+                        float m = __shfl_sync(0xffffffffu, my_m[a], src_lane[q]);
+                        if (q >= cnt) m = 0.0f;
+                        wsum[a] += m;
+#pragma unroll
+                        for (int c = 0; c < NCHUNK; c++)
+#pragma unroll
+                            for (int k = 0; k < VEC; k++) acc[a][c][k] = fmaf(m, x[q][c][k], acc[a][c][k]);
                     }
                 }
             }
+        }
 #pragma unroll
-            for (int q = 0; q < UNROLL; q++) {
+        for (int a = 0; a < NAUG; a++) {
+            const float den = wsum[a] + P.eps;  // model.py:87 / model_mag.py:54
+            float *orow = P.out + ((long long)a * P.B + b) * P.ld_out;
 #pragma unroll
-                for (int a = 0; a < NAUG; a++) {
-                    float m = __shfl_sync(0xffffffffu, my_m[a], src_lane[q]);
-                    if (q >= cnt) m = 0.0f;
-                    wsum[a] += m;
+            for (int c = 0; c < NCHUNK; c++) {
+                const int col = col0 + c * 32 * VEC;
+                if (col < P.F) {
+                    float y[VEC];
 #pragma unroll
-                    for (int c = 0; c < NCHUNK; c++)
-#pragma unroll
-                        for (int k = 0; k < VEC; k++) acc[a][c][k] = fmaf(m, x[q][c][k], acc[a][c][k]);
+                    for (int k = 0; k < VEC; k++) y[k] = acc[a][c][k] / den;
+                    vec_store<VEC>(orow + col, y);
                 }
             }
+            if (P.denom_out && ctile == 0 && lane == 0) P.denom_out[(long long)a * P.B + b] = den;
         }
-    }
-#pragma unroll
-    for (int a = 0; a < NAUG; a++) {
-        const float den = wsum[a] + P.eps;  // model.py:87 / model_mag.py:54
-        float *orow = P.out + ((long long)a * P.B + b) * P.ld_out;
-#pragma unroll
-        for (int c = 0; c < NCHUNK; c++) {
-            const int col = col0 + c * 32 * VEC;
-            if (col < P.F) {
-                float y[VEC];
-#pragma unroll
-                for (int k = 0; k < VEC; k++) y[k] = acc[a][c][k] / den;
-                vec_store<VEC>(orow + col, y);
-            }
-        }
-        if (P.denom_out && ctile == 0 && lane == 0) P.denom_out[(long long)a * P.B + b] = den;
     }
 }
 
@@ -282,10 +314,11 @@ __global__ void __launch_bounds__(kAggBlock) aggregate_fwd_bulk_kernel(AggParams
                 my_nbr = P.nbr ? P.nbr[jj] : (int)jj;
             }
             const bool live = valid && (P.row_ptr != nullptr || s > 0.0f);
+            const unsigned keep_bits = live ? entry_keep_bits(P, jj, NAUG) : 0u;   // one Philox block for all augmentations
 #pragma unroll
             for (int a = 0; a < NAUG; a++) {
                 bool keep = false;
-                my_m[a] = live ? entry_weight(P, jj, a, s, keep) : 0.0f;
+                my_m[a] = live ? entry_weight(P, keep_bits, a, s, keep) : 0.0f;
                 if (valid && P.mask_out && ctile == 0) P.mask_out[(long long)a * P.n_entries + jj] = (live && keep) ? 1 : 0;
                 any |= (my_m[a] != 0.0f);
             }
@@ -482,7 +515,7 @@ __global__ void mask_kernel(long long n, int n_aug, unsigned thresh, int drop_al
 }
 
 // ---------------------------------------------------------------------------------- dispatch
-extern int g_agg_max_vec, g_agg_max_chunk;
+extern int g_agg_max_vec, g_agg_max_chunk, g_agg_waves;
 struct Tiling { int vec, nchunk, n_ctile, tile_cols; };
 
 bool aligned_to(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
@@ -510,8 +543,18 @@ template <int VEC, int NCHUNK, int NAUG>
 int launch_fwd_t(const AggParams &P, cudaStream_t stream) {
     constexpr int UNROLL = NCHUNK == 1 ? 8 : NCHUNK == 2 ? 4 : 2;
     const long long warps = P.B * P.n_ctile;
-    const long long blocks = (warps * 32 + kAggBlock - 1) / kAggBlock;
-    GP_REQUIRE(blocks < (1ll << 31), "batch too large for one launch");
+    long long blocks = (warps * 32 + kAggBlock - 1) / kAggBlock;
+    // persistent warps over the (row, column tile) items: a grid of the resident CTAs ("agg_waves" x occupancy x SMs),
+    // every warp walks several items and prefetches the next item's metadata
+    static int resident = 0, sms = 0;
+    if (resident == 0) {
+        int dev = 0;
+        GP_CUDA_TRY(cudaGetDevice(&dev));
+        GP_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        GP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, aggregate_fwd_kernel<VEC, NCHUNK, NAUG, UNROLL>, kAggBlock, 0));
+        resident = std::max(resident, 1);
+    }
+    if (g_agg_waves > 0) blocks = std::min<long long>(blocks, (long long)sms * resident * g_agg_waves);
     aggregate_fwd_kernel<VEC, NCHUNK, NAUG, UNROLL><<<(unsigned)blocks, kAggBlock, 0, stream>>>(P);
     GP_CUDA_TRY(cudaGetLastError());
     return GP_OK;
@@ -577,6 +620,7 @@ int g_agg_nbuf = 0;       // 0 auto
 int g_agg_max_vec = 2;
 int g_agg_max_chunk = 4;
 int g_agg_smem_kb = 96;   // dynamic shared memory per CTA for the bulk kernel (2 CTAs per SM)
+int g_agg_waves = 1;      // "agg_waves": grid of the register-staged kernel = this many resident waves (0 = one warp per item)
 
 template <int NCHUNK, int NAUG>
 int launch_bulk_t(AggParams P, int nbuf, int buf_stride, int warp_stride, size_t smem, cudaStream_t stream) {
@@ -738,6 +782,7 @@ int gp_set_tuning(const char *key, int64_t value) {
     else if (k == "agg_max_vec") g_agg_max_vec = (int)value;
     else if (k == "agg_max_chunk") g_agg_max_chunk = (int)value;
     else if (k == "agg_smem_kb") g_agg_smem_kb = (int)value;
+    else if (k == "agg_waves") { GP_REQUIRE(value >= 0, "agg_waves must be >= 0"); g_agg_waves = (int)value; }
     else if (k == "push_cluster") {
         GP_REQUIRE(value == -1 || value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16,
                    "push_cluster must be 0 (off), 1 (auto), -1 (one CTA per source), 2, 4, 8 or 16");

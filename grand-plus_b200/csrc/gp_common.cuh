@@ -96,20 +96,22 @@ __host__ __device__ __forceinline__ void gp_philox4x32_10(uint32_t c0, uint32_t 
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// DropNode keep decision for (entry j, augmentation a): one Philox block per 4 consecutive
-// entries, counter = (j/4 lo, j/4 hi, a, offset lo), key = seed ^ (offset hi folded).
-// keep iff u32 >= p * 2^32  (P[keep] = 1-p to within 2^-32).
+// DropNode keep decisions of entry j for up to four augmentations from ONE Philox block: counter = (j lo, j hi, 0,
+// offset lo), key = seed ^ (offset hi folded); augmentation a keeps the entry iff word a >= p * 2^32
+// (P[keep] = 1-p to within 2^-32).  Bit a of the result = keep in augmentation a.
 __host__ __device__ __forceinline__ uint32_t gp_keep_threshold(float p) {
     double t = (double)p * 4294967296.0;
     if (t <= 0.0) return 0u;
     if (t >= 4294967295.0) return 0xFFFFFFFFu;
     return (uint32_t)t;
 }
+__host__ __device__ __forceinline__ uint32_t gp_dropnode_keep4(uint64_t j, uint64_t seed, uint64_t offset, uint32_t thresh) {
+    uint32_t r[4];
+    gp_philox4x32_10((uint32_t)j, (uint32_t)(j >> 32), 0u, (uint32_t)offset,
+                     (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32), r);
+    return (r[0] >= thresh ? 1u : 0u) | (r[1] >= thresh ? 2u : 0u) | (r[2] >= thresh ? 4u : 0u) | (r[3] >= thresh ? 8u : 0u);
+}
 __host__ __device__ __forceinline__ bool gp_dropnode_keep(uint64_t j, uint32_t a, uint64_t seed, uint64_t offset,
                                                           uint32_t thresh) {
-    uint32_t r[4];
-    uint64_t blk = j >> 2;
-    gp_philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), a, (uint32_t)offset,
-                     (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32), r);
-    return r[j & 3] >= thresh;
+    return (gp_dropnode_keep4(j, seed, offset, thresh) >> (a & 3u)) & 1u;
 }

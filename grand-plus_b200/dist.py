@@ -63,7 +63,7 @@ def sum_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
-def gfpush_sharded(graph, node_idx, coef, rmax, K, gather: bool = True):
+def gfpush_sharded(graph, node_idx, coef, rmax, K, gather: bool = True, check: bool = True):
     """GFPush of `node_idx` (identical on every rank) with sources sharded by rank.  Returns the
     device tensors (col int32, val64, val32) for all sources when gather=True (all-gather over
     NCCL/NVLink), else for this rank's shard only, plus the shard bounds."""
@@ -71,7 +71,8 @@ def gfpush_sharded(graph, node_idx, coef, rmax, K, gather: bool = True):
     dev = torch.device("cuda", graph.device)
     nid = torch.as_tensor(node_idx).to(device=dev, dtype=torch.int32)
     lo, hi = shard_range(nid.numel(), rank, ws)
-    _row, col, val, val32 = graph.gfpush_device(nid[lo:hi].contiguous(), coef, rmax, K, want_fp32=True)
+    # check: wait for the shard's push and raise on a device-side refusal before the rows are gathered
+    _row, col, val, val32 = graph.gfpush_device(nid[lo:hi].contiguous(), coef, rmax, K, want_fp32=True, check=check)
     if gather and ws > 1:
         col, val, val32 = all_gather_rows([col, val, val32], nid.numel())
     return col, val, val32, (lo, hi)

@@ -91,8 +91,11 @@ def segments_from_sorted_index(mat_idx: torch.Tensor, check: bool = True):
 def narrow_index(idx: torch.Tensor, n_rows: int) -> torch.Tensor:
     """int64 -> int32 row ids with a range check against n_rows."""
     _need_cuda(idx)
-    if idx.dtype == torch.int32:
-        return idx.contiguous()
+    if idx.dtype == torch.int32:   # already narrow: still range-checked (the kernels index the table with it)
+        idx = idx.contiguous()
+        if idx.numel() and (int(idx.min().item()) < 0 or int(idx.max().item()) >= int(n_rows)):
+            raise IndexError(f"index out of range for a table of {n_rows} rows")
+        return idx
     lib = _lib.load()
     idx = idx.to(torch.int64).contiguous()
     out = torch.empty(idx.numel(), dtype=torch.int32, device=idx.device)
@@ -394,11 +397,12 @@ class PiMatrix:
         self.row_of_node[self.node_idx] = torch.arange(self.S, dtype=torch.int32, device=col.device)
 
     @classmethod
-    def from_graph(cls, graph, node_idx, coef, rmax, K):
-        """Run GFPush on the device and keep the result there."""
+    def from_graph(cls, graph, node_idx, coef, rmax, K, check=True):
+        """Run GFPush on the device and keep the result there.  ``check`` (default) waits for the push and raises if the
+        device refused a source id or a list outgrew its bound, like the host-buffer path does."""
         dev = torch.device("cuda", graph.device)
         nid = torch.as_tensor(node_idx).to(device=dev, dtype=torch.int32)
-        _row, col, _val, val32 = graph.gfpush_device(nid, coef, rmax, K, want_fp32=True)
+        _row, col, _val, val32 = graph.gfpush_device(nid, coef, rmax, K, want_fp32=True, check=check)
         return cls(nid, col, val32, graph.num_nodes)
 
     # -- cache on disk (SURVEY 8f rank 4): the reference recomputes GFPush for every (seed1, seed2) run ---------

@@ -70,8 +70,9 @@ def test_emb_matches_reference_golden():
 # kernel variants reachable through gp_set_tuning: the default (register-staged, 64-bit loads), 128-bit loads, and the
 # TMA-staged cp.async.bulk kernel with two buffer depths -- every one must give the oracle's rows
 AGG_VARIANTS = {"default": {}, "vec4": {"agg_max_vec": 4}, "vec1": {"agg_max_vec": 1}, "bulk": {"agg_kernel": 2},
-                "bulk_nbuf2": {"agg_kernel": 2, "agg_nbuf": 2}, "chunk1": {"agg_max_chunk": 1}}
-AGG_DEFAULTS = {"agg_kernel": 0, "agg_nbuf": 0, "agg_max_vec": 2, "agg_max_chunk": 4, "agg_smem_kb": 96}
+                "bulk_nbuf2": {"agg_kernel": 2, "agg_nbuf": 2}, "chunk1": {"agg_max_chunk": 1},
+                "one_warp_per_item": {"agg_waves": 0}, "waves3": {"agg_waves": 3}}
+AGG_DEFAULTS = {"agg_kernel": 0, "agg_nbuf": 0, "agg_max_vec": 2, "agg_max_chunk": 4, "agg_smem_kb": 96, "agg_waves": 1}
 
 
 @pytest.fixture(params=sorted(AGG_VARIANTS))
@@ -235,6 +236,12 @@ def test_rejects_cpu_tensors_and_unsorted_index():
         gm.random_prop(torch.zeros(4, 3).cuda(), torch.ones(4).cuda(), torch.tensor([0, 1, 0, 1]).cuda(), 0.5)
     with pytest.raises(IndexError):
         gm.random_prop_fused(gm.DeviceFeatures(np.zeros((5, 4), np.float32)), torch.tensor([0, 7]).cuda(),
+                             torch.ones(2).cuda(), torch.tensor([0, 0]).cuda(), 0.5)
+    with pytest.raises(IndexError):   # ids that are already int32 are range-checked too
+        gm.random_prop_fused(gm.DeviceFeatures(np.zeros((5, 4), np.float32)), torch.tensor([0, 7], dtype=torch.int32).cuda(),
+                             torch.ones(2).cuda(), torch.tensor([0, 0]).cuda(), 0.5)
+    with pytest.raises(IndexError):
+        gm.random_prop_fused(gm.DeviceFeatures(np.zeros((5, 4), np.float32)), torch.tensor([-1, 2], dtype=torch.int32).cuda(),
                              torch.ones(2).cuda(), torch.tensor([0, 0]).cuda(), 0.5)
 
 

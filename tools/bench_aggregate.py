@@ -12,11 +12,10 @@ from grandplus_b200 import _lib, model as gm, synth  # noqa: E402
 
 _pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
 PEAK = json.load(open(_pk))["hbm_gbs"] if os.path.exists(_pk) else 6650.0
-DEFAULTS = dict(agg_kernel=0, agg_nbuf=0, agg_max_vec=2, agg_max_chunk=4, agg_smem_kb=96)
-VARIANTS = [("ldg_v2", dict(agg_kernel=1, agg_max_vec=2)), ("ldg_v4", dict(agg_kernel=1, agg_max_vec=4)),
-            ("bulk", dict(agg_kernel=2)), ("bulk_n4", dict(agg_kernel=2, agg_nbuf=4)),
-            ("bulk_n8", dict(agg_kernel=2, agg_nbuf=8)), ("bulk_64k", dict(agg_kernel=2, agg_smem_kb=64)),
-            ("bulk_180k", dict(agg_kernel=2, agg_smem_kb=180))]
+DEFAULTS = dict(agg_kernel=0, agg_nbuf=0, agg_max_vec=2, agg_max_chunk=4, agg_smem_kb=96, agg_waves=1)
+VARIANTS = [("ldg_v2", dict(agg_kernel=1, agg_max_vec=2)), ("w0", dict(agg_kernel=1, agg_waves=0)), ("w2", dict(agg_kernel=1, agg_waves=2)),
+            ("w4", dict(agg_kernel=1, agg_waves=4)), ("ldg_v4", dict(agg_kernel=1, agg_max_vec=4)),
+            ("bulk", dict(agg_kernel=2)), ("bulk_n4", dict(agg_kernel=2, agg_nbuf=4))]
 
 
 def run(N, F, B, K, p, n_aug, reps=15):
@@ -68,5 +67,6 @@ if __name__ == "__main__":
     for cfg in [(232965, 602, 16384, 32, 0.5, 2), (232965, 602, 16384, 32, 0.0, 1), (232965, 602, 131072, 32, 0.5, 2),
                 (2449029, 100, 16384, 64, 0.5, 2), (2449029, 100, 131072, 64, 0.5, 2), (2449029, 100, 131072, 64, 0.0, 1),
                 (2708, 1433, 2708, 32, 0.5, 2), (19717, 500, 19717, 16, 0.5, 2), (1000000, 64, 131072, 32, 0.5, 2),
+                (10541560, 64, 16384, 32, 0.5, 2),
                 (232965, 602, 250, 64, 0.5, 2)]:
         run(*cfg)
