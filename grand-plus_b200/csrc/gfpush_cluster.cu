@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                             if (base + CB * q < len) sink(vp[q], add, ok[q]);
                     }
                 }
-                if (n_big) __syncthreads();
+                __syncthreads();   // (also orders every thread's read of n_big before its reset below)
             }
             if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; }
             GPC_PHASE(1);
