@@ -41,7 +41,8 @@ class PushStats(ctypes.Structure):
                 ("support_total", ctypes.c_int64), ("sources", ctypes.c_int64), ("ctas", ctypes.c_int64),
                 ("scratch_bytes", ctypes.c_int64), ("scratch_mode", ctypes.c_int32),
                 ("kernel_launches", ctypes.c_int32), ("cluster_sources", ctypes.c_int64),
-                ("redo_sources", ctypes.c_int64), ("cluster_size", ctypes.c_int32), ("table_slots", ctypes.c_int32)]
+                ("redo_sources", ctypes.c_int64), ("cluster_size", ctypes.c_int32), ("table_slots", ctypes.c_int32),
+                ("bucket_count", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -18,8 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "_obj")
 LIB_PATH = os.path.join(_HERE, "libgrandplus_b200.so")
-SOURCES = ["capi.cu", "gfpush.cu", "gfpush_cluster.cu", "aggregate.cu", "emb.cu"]
-HEADERS = [os.path.join(CSRC, "gp_common.cuh"), os.path.join(CSRC, "gfpush_shared.cuh"), os.path.join(CSRC, "gfpush_cluster.h"), os.path.join(os.path.dirname(_HERE), "include", "grandplus_b200.h")]
+SOURCES = ["capi.cu", "gfpush.cu", "gfpush_cluster.cu", "gfpush_bucket.cu", "aggregate.cu", "emb.cu"]
+HEADERS = [os.path.join(CSRC, "gp_common.cuh"), os.path.join(CSRC, "gfpush_shared.cuh"), os.path.join(CSRC, "gfpush_cluster.h"), os.path.join(CSRC, "gfpush_bucket.h"), os.path.join(os.path.dirname(_HERE), "include", "grandplus_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -28,6 +28,7 @@
 #include "gp_common.cuh"
 #include "gfpush_shared.cuh"
 #include "gfpush_cluster.h"
+#include "gfpush_bucket.h"
 
 #include <cooperative_groups.h>
 
@@ -50,6 +51,9 @@ int g_push_cluster = 0;       // "push_cluster": the cluster kernel (gfpush_clus
 int g_push_cluster_probe = 128;   // "push_cluster_probe": 4-key buckets tried before a source is handed to the slab kernel
                                   // (at the loads the planner aims at the longest probe sequence is a few buckets)
 int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree are expanded by the whole cluster (0 = 64 x G)
+int g_push_bucket = 1;        // "push_bucket": the hash-bucket kernel (gfpush_bucket.cu) for supports far beyond shared memory:
+                              // 0 off, 1 auto (where the slab kernel would run), 2 always
+int g_push_bucket_nb = 0;     // "push_bucket_nb": buckets per source (rounded up to a power of two); 0 = from the expected support
 int g_push_max_clusters = 0;  // "push_max_clusters": cap on the resident clusters (0 = all the device schedules); scaling experiments
 int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments
 int g_push_tuning_gen = 0;    // bumped by gp_set_tuning so that handles re-plan
@@ -835,6 +839,14 @@ struct gp_graph {
     int idbits = 32;
     void *cscratch = nullptr;
     size_t cscratch_bytes = 0;
+    void *bscratch = nullptr;   // bucket kernel: per-CTA pair streams, reserve logs, push list, merged reserve
+    size_t bscratch_bytes = 0;
+    // largest support of a source measured on this handle, and the (L, rmax) it was measured for: sizes the hash buckets
+    long long support_hint = 0;
+    int hint_L = 0;
+    double hint_rmax = 0.0;
+    int cur_L = 0;              // parameters of the last push (collect_stats files its measurement under them)
+    double cur_rmax = 0.0;
     int max_clusters[5] = {-1, -1, -1, -1, -1};   // resident clusters of 1, 2, 4, 8, 16 CTAs (-1 = not asked yet)
     // orders a push after the previous one on this handle when the two run on different streams
     cudaEvent_t ev_done = nullptr;
@@ -1091,6 +1103,61 @@ int plan_cluster(gp_graph *g, long long S, int L, double rmax, int K, long long 
     return GP_OK;
 }
 
+// ---- bucket kernel: planning -------------------------------------------------------------------------
+constexpr long long kPilotMinSources = 2048;   // calls with fewer sources are not worth the pilot's synchronisation
+struct BucketPlan {
+    int nb = 0, log_nb = 0;
+    long long ctas = 0, capPair = 0, capLog = 0, capP = 0, capS = 0;
+    size_t bytes = 0;
+    size_t off_pi = 0, off_pv = 0, off_li = 0, off_lv = 0, off_ps = 0, off_pl = 0, off_pa = 0, off_si = 0, off_sv = 0;
+};
+
+// The bucket kernel replaces the slab kernel as the first pass where the slabs would run (supports far beyond the
+// shared-memory table) and the bucket counters fit shared memory; the slabs then only take what it hands over.
+void plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, long long support_hint, BucketPlan *bp) {
+    *bp = BucketPlan{};
+    if (g_push_bucket == 0) return;
+    if (g_push_bucket == 1 && pl.hslots > 0) return;   // the shared-memory table tier takes this call
+    const long long n = g->n;
+    // a level pushes at most min(nnz + n, 1/rmax) edges
+    long long capE = g->nnz + n;
+    if (rmax > 0.0) capE = (long long)std::min<double>((double)capE, std::ceil(1.0 / rmax * 1.0001) + 16.0);
+    // buckets: a power of two >= 2 such that the LARGEST support seen on this handle for these parameters (a pilot launch
+    // measures it, push_device_locked) loads the table to <= 0.8; without a measurement the a-priori bound min(n, 1.5 x the
+    // per-level edge bound) stands in, which is several times too large on the BASELINE shapes: more and smaller visits
+    // than necessary, but never an overflow.  A source that outgrows the table anyway is handed to the slab kernel.
+    long long nb = 2;
+    if (g_push_bucket_nb > 0) {
+        while (nb < g_push_bucket_nb && nb < kBucketMaxBuckets) nb *= 2;
+    } else {
+        const long long est = support_hint > 0 ? support_hint + support_hint / 16 : std::min<long long>(n, capE + capE / 2);
+        while (nb < kBucketMaxBuckets && est > nb * (kBucketSlots * 4ll / 5)) nb *= 2;
+    }
+    int log_nb = 0;
+    while ((1ll << log_nb) < nb) log_nb++;
+    bp->nb = (int)nb; bp->log_nb = log_nb;
+    bp->ctas = g->num_sms;
+    // a bucket stream holds four times its even share of a level (and at least 4096 pairs)
+    bp->capPair = std::min<long long>(capE, std::max<long long>(4096, 4 * capE / nb));
+    // the reserve log holds one entry per frontier node and level: at most 1 + (L-1) * capF in all
+    bp->capLog = std::min<long long>(1 + (long long)std::max(L - 1, 0) * pl.capF + 16, std::max<long long>(4096, 4 * capE / nb));
+    bp->capP = pl.capF * 2 + 4096;   // push entries are cut into 128-edge chunks: at most capF nodes + capE / 128 chunks
+    // the merged reserve: one slot per node of the support
+    bp->capS = std::min<long long>(n, 1 + (long long)std::max(L - 1, 0) * pl.capF) + 16;
+    const size_t c = (size_t)bp->ctas;
+    size_t o = 0;
+    bp->off_pi = o; o += align_up(c * nb * bp->capPair * 4, 256);
+    bp->off_pv = o; o += align_up(c * nb * bp->capPair * 8, 256);
+    bp->off_li = o; o += align_up(c * nb * bp->capLog * 4, 256);
+    bp->off_lv = o; o += align_up(c * nb * bp->capLog * 8, 256);
+    bp->off_ps = o; o += align_up(c * bp->capP * 4, 256);
+    bp->off_pl = o; o += align_up(c * bp->capP * 4, 256);
+    bp->off_pa = o; o += align_up(c * bp->capP * 8, 256);
+    bp->off_si = o; o += align_up(c * bp->capS * 4, 256);
+    bp->off_sv = o; o += align_up(c * bp->capS * 8, 256);
+    bp->bytes = o;
+}
+
 // CSR entries with the degree code in the spare high bits (built once per handle, on first use).
 int ensure_packed(gp_graph *g, cudaStream_t stream) {
     if (g->d_packed) return GP_OK;
@@ -1115,6 +1182,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     GP_REQUIRE(coef != nullptr, "coef is null");
     GP_REQUIRE(!(rmax != rmax), "rmax is NaN");
     g->last = gp_push_stats{};
+    g->cur_L = L; g->cur_rmax = rmax;
     if (S == 0) return GP_OK;
     GP_REQUIRE(d_node_idx && d_row && d_col && d_val, "null device buffer");
     // Every push on a handle shares the control block, the coefficient array and the scratch: a push on another stream
@@ -1124,10 +1192,16 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     int rc = make_plan(g, S, L, rmax, false, &pl);
     if (rc != GP_OK) return rc;
     ClusterPlan cp{};
+    BucketPlan bp{};
+    bool pilot = false;
     if (pl.mode == GP_SCRATCH_HBM) {
         rc = plan_cluster(g, S, L, rmax, K, pl.capF, &cp);
         if (rc != GP_OK) return rc;
-        if (cp.G > 0) {   // the slabs only back the cluster kernel up
+        const bool have_hint = g->support_hint > 0 && g->hint_L == L && g->hint_rmax == rmax;
+        if (cp.G == 0) plan_bucket(g, S, L, rmax, pl, have_hint ? g->support_hint : 0, &bp);
+        // no measurement yet and enough sources to pay for one: the first sources run as a pilot (below)
+        pilot = bp.nb > 0 && !have_hint && g_push_bucket_nb == 0 && S >= kPilotMinSources;
+        if (cp.G > 0 || bp.nb > 0) {   // the slabs only back the first-pass kernel up
             rc = make_plan(g, S, L, rmax, true, &pl);
             if (rc != GP_OK) return rc;
         }
@@ -1200,6 +1274,62 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
         launches++;
         // second pass: what outgrew the tables or the streams, on the slabs (exits at once when the list is empty)
         P.redo = g->d_redo; P.redo_count = g->d_ctrl + 6;
+    } else if (bp.nb > 0) {
+        rc = ensure_packed(g, stream);
+        if (rc != GP_OK) return rc;
+        if (g->d_redo_cap < (size_t)S) {
+            GP_CUDA_TRY(cudaStreamSynchronize(stream));
+            if (g->ev_recorded) GP_CUDA_TRY(cudaEventSynchronize(g->ev_done));
+            cudaFree(g->d_redo); g->d_redo = nullptr; g->d_redo_cap = 0;
+            GP_CUDA_TRY(cudaMalloc(&g->d_redo, sizeof(int) * (size_t)S));
+            g->d_redo_cap = (size_t)S;
+        }
+        auto launch_bucket = [&](const BucketPlan &b, long long first, long long last) -> int {
+            if (g->bscratch_bytes < b.bytes) {
+                GP_CUDA_TRY(cudaStreamSynchronize(stream));
+                if (g->ev_recorded) GP_CUDA_TRY(cudaEventSynchronize(g->ev_done));
+                cudaFree(g->bscratch); g->bscratch = nullptr; g->bscratch_bytes = 0;
+                GP_CUDA_TRY(cudaMalloc(&g->bscratch, b.bytes));
+                g->bscratch_bytes = b.bytes;
+            }
+            char *bb = (char *)g->bscratch;
+            BucketPushParams B{};
+            B.node_rec = g->d_node_rec; B.packed = g->d_packed; B.n = (int)g->n; B.idbits = g->idbits; B.nb = b.nb; B.log_nb = b.log_nb;
+            B.max_probe = std::max(g_push_cluster_probe, 1);
+            B.node_idx = d_node_idx; B.S = last; B.it_base = first; B.coef = g->d_coef; B.L = L; B.rmax = rmax; B.K = K;
+            B.out_row = d_row; B.out_col = d_col; B.out_val = d_val; B.out_val32 = d_val32;
+            B.pair_id = (int *)(bb + b.off_pi); B.pair_val = (double *)(bb + b.off_pv); B.capPair = b.capPair;
+            B.log_id = (int *)(bb + b.off_li); B.log_val = (double *)(bb + b.off_lv); B.capLog = b.capLog;
+            B.push_start = (int *)(bb + b.off_ps); B.push_len = (int *)(bb + b.off_pl); B.push_add = (double *)(bb + b.off_pa);
+            B.capP = b.capP;
+            B.sup_id = (int *)(bb + b.off_si); B.sup_val = (double *)(bb + b.off_sv); B.capS = b.capS;
+            B.queue = g->d_ctrl; B.stats = g->d_ctrl + 1; B.cum = g->d_ctrl + 16; B.phase = g->d_ctrl + 24;
+            B.max_support = g->d_ctrl + 8;
+            B.redo = g->d_redo; B.redo_count = g->d_ctrl + 6;
+            launches++;
+            return gpb_launch(B, (int)std::min<long long>(b.ctas, last - first), stream);
+        };
+        long long first = 0;
+        if (pilot) {
+            // Pilot: two sources per SM with the a-priori bucket count, then read the largest support back (the one
+            // synchronisation of the first call on a handle) and size the buckets of the rest -- and of later calls -- from it.
+            first = std::min<long long>(S, 2ll * g->num_sms);
+            rc = launch_bucket(bp, 0, first);
+            if (rc != GP_OK) return rc;
+            unsigned long long h_max = 0;
+            GP_CUDA_TRY(cudaMemcpyAsync(&h_max, g->d_ctrl + 8, sizeof h_max, cudaMemcpyDeviceToHost, stream));
+            GP_CUDA_TRY(cudaStreamSynchronize(stream));
+            if (h_max > 0) {
+                g->support_hint = (long long)h_max; g->hint_L = L; g->hint_rmax = rmax;
+                plan_bucket(g, S, L, rmax, pl, g->support_hint, &bp);
+            }
+            GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long), stream));   // the queue restarts at `first`
+        }
+        if (first < S) {
+            rc = launch_bucket(bp, first, S);
+            if (rc != GP_OK) return rc;
+        }
+        P.redo = g->d_redo; P.redo_count = g->d_ctrl + 6;
     }
     rc = launch_slab(P, pl, stream);
     if (rc != GP_OK) return rc;
@@ -1208,18 +1338,24 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     g->ev_recorded = true;
     g->epoch_base += S;
     g->last.sources = S;
-    g->last.ctas = cp.G > 0 ? (long long)cp.clusters * cp.G : std::min<long long>(pl.ctas, S);
-    g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->cscratch_bytes);
+    g->last.ctas = cp.G > 0 ? (long long)cp.clusters * cp.G : bp.nb > 0 ? std::min<long long>(bp.ctas, S) : std::min<long long>(pl.ctas, S);
+    g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->cscratch_bytes + g->bscratch_bytes);
     g->last.scratch_mode = pl.mode; g->last.kernel_launches = launches; g->last.cluster_size = cp.G;
-    g->last.table_slots = cp.G > 0 ? kClusterSlots : pl.hslots;
+    g->last.table_slots = cp.G > 0 ? kClusterSlots : bp.nb > 0 ? kBucketSlots : pl.hslots;
+    g->last.bucket_count = bp.nb;
     return GP_OK;
 }
 
 // Reads the control block back (synchronises `stream`) and turns device-side flags into errors.
 int collect_stats(gp_graph *g, cudaStream_t stream) {
-    unsigned long long h[8];
+    unsigned long long h[9];
     GP_CUDA_TRY(cudaMemcpyAsync(h, g->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, stream));
     GP_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (g->last.bucket_count > 0 && h[8] > 0) {   // the largest support of the call sizes the buckets of the next one
+        const bool same = g->hint_L == g->cur_L && g->hint_rmax == g->cur_rmax;
+        g->support_hint = same ? std::max<long long>(g->support_hint, (long long)h[8]) : (long long)h[8];
+        g->hint_L = g->cur_L; g->hint_rmax = g->cur_rmax;
+    }
     g->last.edges_pushed = (int64_t)h[1];
     g->last.frontier_total = (int64_t)h[2];
     g->last.support_total = (int64_t)h[3];
@@ -1322,7 +1458,7 @@ void gp_graph_destroy(gp_graph *g) {
     if (g->ev_recorded) cudaEventSynchronize(g->ev_done);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->owns_csr) { cudaFree(g->d_indptr); cudaFree(g->d_indices); }
-    cudaFree(g->d_node_rec); cudaFree(g->d_packed); cudaFree(g->scratch); cudaFree(g->cscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
+    cudaFree(g->d_node_rec); cudaFree(g->d_packed); cudaFree(g->scratch); cudaFree(g->cscratch); cudaFree(g->bscratch); cudaFree(g->d_redo); cudaFree(g->d_coef); cudaFree(g->d_ctrl); cudaFree(g->d_node); cudaFree(g->d_out);
     if (g->ev_done) cudaEventDestroy(g->ev_done);
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;

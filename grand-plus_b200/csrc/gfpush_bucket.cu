@@ -1,0 +1,587 @@
+// gfpush_bucket.cu -- GFPush + top-k for supports FAR beyond shared memory (Amazon2M-shape: 152 K nodes per source):
+// accumulate by HASH BUCKETS, one bucket at a time in a shared-memory table, instead of random read-modify-writes in HBM.
+// Same computation as gfpush.cu (Graph::gfpush_omp, /root/reference/precompute/graph.h:53-131), one CTA per source.
+//
+// The slab kernel (gfpush.cu MODE 0) touches one 16-byte slot per pushed edge and per settled node at a random HBM
+// address: a 64-byte fetch and a 32-byte write-back for 8 useful bytes, 62 MB of DRAM traffic per Amazon2M-shape source
+// (11 x the algorithmic bytes), bound by the DRAM random-access rate (profiles/r02_gfpush.md).  Here
+//   * expand APPENDS every pushed edge (packed node, r/deg) to the stream of the node's bucket, bucket = the top bits of
+//     hash(node) (nb = 2^k buckets, chosen so that a source's support per bucket fits the table at a load of ~0.6;
+//     one shared-memory counter per bucket; chunks of 128 edges per warp, coalesced CSR reads, no owner search);
+//   * a level is then settled bucket by bucket: the bucket's pairs are read back coalesced (thousands per visit, several per
+//     thread) and accumulated into a 16 384-slot open-addressed {key, residue} table in shared memory; every thread then
+//     scans its 16 slots: reserve += coef * r is appended to the bucket's reserve log, the push decision uses the degree
+//     code carried in the key (gfpush.cu) and fetches {start, degree} only for the few nodes that pass, and the slot is
+//     emptied for the next bucket;
+//   * after the last level the reserve logs are merged bucket by bucket through the same table into compact
+//     (node, reserve) arrays, from which the K largest are selected (threshold = the K-th largest lane maximum, then a
+//     radix select over the survivors; gfpush_shared.cuh).
+// All streams are written and read coalesced; nothing is read-modify-written in HBM.  (A first version used node-RANGE
+// buckets with a dense window: 150 buckets of ~1 000 pairs per level made every visit a 2 us latency chain for one pair per
+// thread, 70 K rows/s; profiles/r02_gfpush.md.)  A source whose bucket stream or table overflows is handed to the slab
+// kernel through the redo list.
+#include "gfpush_bucket.h"
+#include "gfpush_shared.cuh"
+
+#include <algorithm>
+
+namespace gpp {
+namespace {
+
+constexpr int BB = kBucketBlock;
+constexpr int kSlots = kBucketSlots;    // slots of the shared-memory table
+constexpr int kBuckets4 = kSlots / 4;   // 4-key buckets of the table: one 16-byte shared-memory read per probe
+constexpr int SPT = kSlots / BB;        // table slots per thread in the scan
+constexpr int kEmpty = -1;
+constexpr int kChunk = 128;             // edges per push-list entry
+constexpr int kBigLen = 4096;           // longer entries stay whole and are expanded by all warps together
+constexpr int kBigCap = 32;
+constexpr int kItemBatch = 2;
+constexpr int kCandCap = 1024;
+constexpr int kGroupPairs = kSlots * 5 / 8;   // buckets are visited together while their pairs stay below this table load
+
+__device__ __forceinline__ unsigned hash_node(unsigned id) { return id * 2654435761u; }
+
+// Slot of packed node `vp` in the table (claiming one when it is new), or -1 when `max_probe` buckets hold neither it nor an
+// empty slot.  Keys are never removed while a bucket is live and empties are taken in index order, so an observed key is final.
+__device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int max_probe, bool &claimed) {
+    unsigned b = bucket;
+    claimed = false;
+    for (int probe = 0; probe < max_probe; probe++, b = (b + 1) & (kBuckets4 - 1)) {
+        const int4 k4 = *reinterpret_cast<const int4 *>(keys + 4 * b);
+        const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int k = kk[i];
+            if (k == kEmpty) {
+                k = atomicCAS(keys + 4 * b + i, kEmpty, vp);
+                if (k == kEmpty) { claimed = true; return (int)(4 * b + i); }
+            }
+            if (k == vp) return (int)(4 * b + i);
+        }
+    }
+    return -1;
+}
+
+struct BSmem {
+    int start[BB];             // push list of the level: first BB entries {start, len, add}; during the top-k (the list is
+                               // dead then) `add` / `start` hold the survivors of the pre-filter
+    unsigned len[BB];
+    double add[BB];
+    unsigned warp_scan[BB / 32 + 1];
+    double wtau[BB / 32];
+    union {
+        struct {
+            unsigned hist[kHistBins];
+            unsigned long long bkey[kBucketCap];
+            int bid[kBucketCap];
+        } sel;
+        struct {
+            double r[kCandCap];
+            unsigned key[kCandCap];
+        } cand;
+    };
+    long long it;
+    int n_push, n_sel, n_sup, n_list, next_item, n_big;
+    int big_st[kBigCap];
+    unsigned big_len[kBigCap];
+    double big_add[kBigCap];
+    int n_out, n_bucket;
+    int sel_bin, sel_above, sel_inbin;
+    int ovf;
+    int full;                  // a probe sequence ran out: the source goes to the slab kernel, stop probing
+    long long tau_bits;
+    long long ph[8], t_prev;
+};
+
+__global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushParams P) {
+    __shared__ BSmem sm;
+    extern __shared__ __align__(16) double s_vals[];                                  // [kSlots] the bucket's residues / reserves
+    int *s_keys = reinterpret_cast<int *>(s_vals + kSlots);             // [kSlots] packed node, kEmpty = free
+    unsigned *s_cnt = reinterpret_cast<unsigned *>(s_keys + kSlots);    // [nb] pairs per bucket (this level)
+    unsigned *s_lcnt = s_cnt + P.nb;                                    // [nb] reserve-log entries per bucket (this source)
+    const int bshift = 32 - P.log_nb;                                   // hash >> bshift = bucket (log_nb >= 1)
+
+    const int tid = threadIdx.x;
+    const int lane = gp_lane();
+    const long long cta = blockIdx.x;
+    const unsigned idmask = P.idbits >= 32 ? 0xFFFFFFFFu : ((1u << P.idbits) - 1u);
+    const bool has_code = P.idbits < 32;
+    int *pair_id = P.pair_id + cta * P.nb * P.capPair;
+    double *pair_val = P.pair_val + cta * P.nb * P.capPair;
+    int *log_id = P.log_id + cta * P.nb * P.capLog;
+    double *log_val = P.log_val + cta * P.nb * P.capLog;
+    int *push_start = P.push_start + cta * P.capP;
+    int *push_len = P.push_len + cta * P.capP;
+    double *push_add = P.push_add + cta * P.capP;
+    int *sup_id = P.sup_id + cta * P.capS;
+    double *sup_val = P.sup_val + cta * P.capS;
+    unsigned long long *err = P.stats + 3;
+
+    for (int i = tid; i < kSlots; i += BB) { s_vals[i] = 0.0; s_keys[i] = kEmpty; }
+    for (int i = tid; i < P.nb; i += BB) { s_cnt[i] = 0; s_lcnt[i] = 0; }
+    if (tid == 0) {
+        sm.n_push = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; sm.ovf = 0; sm.full = 0;
+        for (int i = 0; i < 8; i++) sm.ph[i] = 0;
+    }
+    unsigned long long st_sources = 0, st_redo = 0;      // thread 0
+    unsigned long long st_edges = 0;                      // lane 0 of every warp
+    unsigned long long st_frontier = 0, st_support = 0;   // every thread
+    const long long t_begin = clock64();
+    if (tid == 0) sm.t_prev = t_begin;
+#define GPB_PHASE(i) do { if (tid == 0) { const long long t_now = clock64(); sm.ph[i] += t_now - sm.t_prev; sm.t_prev = t_now; } } while (0)
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.it = P.it_base + (long long)atomicAdd(P.queue, 1ull);
+        __syncthreads();
+        const long long it = sm.it;
+        if (it >= P.S) break;
+        const int src = P.node_idx[it];
+        if (src < 0 || src >= P.n) {   // refuse instead of reading out of bounds
+            if (tid == 0) atomicOr(err, kErrBadSource);
+            for (int i = tid; i < P.K; i += BB) {
+                const long long o = it * P.K + i;
+                P.out_row[o] = 0; P.out_col[o] = 0; P.out_val[o] = 0.0;
+                if (P.out_val32) P.out_val32[o] = 0.f;
+            }
+            continue;
+        }
+        const int2 src_rec = __ldg(P.node_rec + src);
+        int src_key = src;
+        if (has_code) {
+            const unsigned cap = (1u << (31 - P.idbits)) - 1u;
+            src_key = (int)((unsigned)src | (min((unsigned)src_rec.y, cap) << P.idbits));
+        }
+        unsigned src_front = 0;
+        unsigned long long src_edges = 0;
+        bool ovf = false;
+
+        // A push-list entry {start, len, add = r / deg}, cut into chunks of kChunk edges (the unit one warp expands).
+        auto add_entry = [&](int e_start, unsigned e_len, double e_add) {
+            const unsigned step = e_len > (unsigned)kBigLen ? e_len : (unsigned)kChunk;
+            for (unsigned o = 0; o < e_len; o += step) {
+                const int p = atomicAdd(&sm.n_push, 1);
+                const unsigned l = min(step, e_len - o);
+                if (p < BB) { sm.start[p] = e_start + (int)o; sm.len[p] = l; sm.add[p] = e_add; }
+                else if (p < P.capP) { push_start[p] = e_start + (int)o; push_len[p] = (int)l; push_add[p] = e_add; }
+                else ovf = true;
+            }
+        };
+        // Exact push decision of a node whose degree code allows it (graph.h:91-95).
+        auto consider = [&](unsigned key, double r) {
+            const int2 rec = __ldg(P.node_rec + (key & idmask));
+            const unsigned d = (unsigned)rec.y;
+            if (d == 0) add_entry(-1, 1u, r);                                      // graph.h:91-93: back to the source
+            else if (r >= P.rmax * (double)d) add_entry(rec.x, d, r / (double)d);   // graph.h:94-95
+        };
+        // Adds the pairs (ids[i], vals[i]), i < n, into the table (graph.h:98 / :106).  The kernel is bound by the latency
+        // of dependent shared-memory operations (32 warps per SM, each find-or-claim + add is a chain of four), so a thread
+        // takes its pairs four at a time and runs every step for all four before the next one: four key-bucket reads, four
+        // claims, four adds are in flight together.  The home bucket settles ~9 of 10 pairs; the rest take find_slot.
+        auto accumulate = [&](const int *ids, const double *vals, const unsigned n, const int max_probe) {
+            for (unsigned i0 = tid; i0 < n; i0 += BB * 4) {
+                int vp[4];
+                double av[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned i = i0 + BB * q;
+                    vp[q] = kEmpty; av[q] = 0.0;   // (kEmpty is not a node: the pair is skipped below)
+                    if (i < n) { vp[q] = __ldcs(ids + i); av[q] = __ldcs(vals + i); }
+                }
+                if (*(volatile int *)&sm.full) break;
+                int at[4];     // slot of the key / of the first free slot in the home bucket
+                int st[4];     // 0 skip, 1 key found, 2 free slot to claim, 3 bucket holds other keys only
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - 12)) & (kBuckets4 - 1);
+                    const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * hb);
+                    const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+                    at[q] = 4 * (int)hb; st[q] = 3;
+#pragma unroll
+                    for (int i = 3; i >= 0; i--) {   // (free slots are taken in index order: the first free one ends the search)
+                        if (kk[i] == vp[q]) { st[q] = 1; at[q] = 4 * (int)hb + i; }
+                        else if (kk[i] == kEmpty) { st[q] = 2; at[q] = 4 * (int)hb + i; }
+                    }
+                    if (vp[q] == kEmpty) st[q] = 0;
+                }
+                int won[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    won[q] = 0;
+                    if (st[q] == 2) won[q] = atomicCAS(s_keys + at[q], kEmpty, vp[q]);
+                }
+                unsigned long long old[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    old[q] = 1ull;
+                    if (st[q] == 2) {
+                        if (won[q] == kEmpty) old[q] = atomicCAS(reinterpret_cast<unsigned long long *>(s_vals + at[q]), 0ull, (unsigned long long)__double_as_longlong(av[q]));
+                        else if (won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (st[q] == 3) {
+                        bool claimed;
+                        at[q] = find_slot(s_keys, (unsigned)at[q] >> 2, vp[q], max_probe, claimed);
+                        if (at[q] < 0) { ovf = true; sm.full = 1; st[q] = 0; }
+                    }
+                    if (st[q] != 0 && old[q] != 0ull) atomicAdd(s_vals + at[q], av[q]);
+                }
+            }
+        };
+        // ------------------------------------------------------------------ level 0 (graph.h:80-82)
+        const unsigned deg0 = (unsigned)src_rec.y;
+        const bool push0 = P.L > 1 && (deg0 == 0 || 1.0 >= P.rmax * (double)deg0);
+        if (tid == 0) {
+            st_sources++;
+            sm.n_push = 0;
+            if (push0) {
+                if (deg0 == 0) add_entry(-1, 1u, 1.0);
+                else add_entry(src_rec.x, deg0, 1.0 / (double)deg0);
+            }
+        }
+        if (tid == 0) {   // reserve[src] = coef[0] * 1: the first entry of the log of the source's bucket
+            const unsigned b0 = hash_node((unsigned)src) >> bshift;
+            log_id[(long long)b0 * P.capLog] = src_key; log_val[(long long)b0 * P.capLog] = P.coef[0];
+            s_lcnt[b0] = 1;
+            src_front++;
+        }
+        __syncthreads();
+        GPB_PHASE(0);
+
+        for (int level = 0; level < P.L - 1; level++) {   // graph.h:83
+            const int n_items = min((long long)sm.n_push, P.capP);
+            if (n_items == 0) break;   // nothing pushes: every later residue is zero (the reserve is complete)
+            // ---------------------------------------------------------------- expand (graph.h:94-100): append to the buckets
+            // Reserve a position in the node's bucket stream / store the pair there: split so that a batch of edges issues all
+            // its counter updates before the first dependent store.
+            auto reserve = [&](const int vp, const bool ok, unsigned &b) -> unsigned {
+                b = hash_node((unsigned)vp & idmask) >> bshift;
+                return ok ? atomicAdd(&s_cnt[b], 1u) : 0u;
+            };
+            auto store = [&](const int vp, const double av, const bool ok, const unsigned b, const unsigned pos) {
+                if (ok) {
+                    if (pos < (unsigned)P.capPair) { pair_id[(long long)b * P.capPair + pos] = vp; pair_val[(long long)b * P.capPair + pos] = av; }
+                    else ovf = true;
+                }
+            };
+            auto sink = [&](const int vp, const double av, const bool ok) {
+                unsigned b;
+                const unsigned pos = reserve(vp, ok, b);
+                store(vp, av, ok, b, pos);
+            };
+            auto load_item = [&](const int i, int &st, unsigned &len, double &add) {
+                st = 0; len = 0; add = 0.0;
+                if (i < n_items) {
+                    if (i < BB) { st = sm.start[i]; len = sm.len[i]; add = sm.add[i]; }
+                    else { st = push_start[i]; len = (unsigned)push_len[i]; add = push_add[i]; }
+                }
+            };
+            for (;;) {
+                int i0 = 0;
+                if (lane == 0) i0 = atomicAdd(&sm.next_item, kItemBatch);
+                i0 = __shfl_sync(0xffffffffu, i0, 0);
+                if (i0 >= n_items) break;
+                int st[kItemBatch];
+                unsigned len[kItemBatch];
+                double add[kItemBatch];
+#pragma unroll
+                for (int k = 0; k < kItemBatch; k++) {
+                    load_item(i0 + k, st[k], len[k], add[k]);
+                    if (lane == 0) src_edges += len[k];
+                    if (len[k] > (unsigned)kChunk) {   // an uncut (long) entry: all warps expand it together after this pass
+                        int bpos = 0;
+                        if (lane == 0) bpos = atomicAdd(&sm.n_big, 1);
+                        bpos = __shfl_sync(0xffffffffu, bpos, 0);
+                        if (bpos < kBigCap) {
+                            if (lane == 0) { sm.big_st[bpos] = st[k]; sm.big_len[bpos] = len[k]; sm.big_add[bpos] = add[k]; }
+                        } else {
+                            for (unsigned base = 0; base < len[k]; base += 32) {
+                                const bool ok = base + lane < len[k];
+                                int v = src_key;
+                                if (ok && st[k] >= 0) v = __ldcs(P.packed + st[k] + base + lane);
+                                sink(v, add[k], ok);
+                            }
+                        }
+                        len[k] = 0;
+                    }
+                }
+                int vp[kItemBatch][kChunk / 32];
+#pragma unroll
+                for (int k = 0; k < kItemBatch; k++) {
+#pragma unroll
+                    for (int q = 0; q < kChunk / 32; q++) {
+                        vp[k][q] = src_key;
+                        if (st[k] >= 0 && (unsigned)(32 * q + lane) < len[k]) vp[k][q] = __ldcs(P.packed + st[k] + 32 * q + lane);   // graph.h:96-97
+                    }
+                }
+                unsigned bk[kItemBatch][kChunk / 32], ps[kItemBatch][kChunk / 32];
+#pragma unroll
+                for (int k = 0; k < kItemBatch; k++) {
+#pragma unroll
+                    for (int q = 0; q < kChunk / 32; q++) ps[k][q] = reserve(vp[k][q], (unsigned)(32 * q + lane) < len[k], bk[k][q]);
+                }
+#pragma unroll
+                for (int k = 0; k < kItemBatch; k++) {
+#pragma unroll
+                    for (int q = 0; q < kChunk / 32; q++) store(vp[k][q], add[k], (unsigned)(32 * q + lane) < len[k], bk[k][q], ps[k][q]);
+                }
+            }
+            __syncthreads();
+            {
+                const int n_big = min(sm.n_big, kBigCap);
+                for (int bi = 0; bi < n_big; bi++) {
+                    const int st = sm.big_st[bi];
+                    const unsigned len = sm.big_len[bi];
+                    const double add = sm.big_add[bi];
+                    for (unsigned base0 = 0; base0 < len; base0 += BB * 4) {   // (uniform trip count: sink is a warp operation)
+                        const unsigned base = base0 + tid;
+                        int vp[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const unsigned e = base + BB * q;
+                            vp[q] = src_key;
+                            if (e < len && st >= 0) vp[q] = __ldcs(P.packed + st + e);
+                        }
+                        unsigned bk[4], ps[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) ps[q] = reserve(vp[q], base + BB * q < len, bk[q]);
+#pragma unroll
+                        for (int q = 0; q < 4; q++) store(vp[q], add, base + BB * q < len, bk[q], ps[q]);
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; }
+            GPB_PHASE(1);
+            // ---------------------------------------------------------------- settle of level + 1, bucket by bucket
+            const int nl = level + 1;
+            const bool will_push = nl < P.L - 1;
+            const double c = P.coef[nl];
+            for (int b = 0; b < P.nb;) {
+                // one visit = consecutive buckets [b, e) whose pairs together cannot overfill the table (pairs bound the
+                // distinct nodes); a bucket above the limit is a visit of its own.  (s_cnt is stable since the barrier that
+                // ended the expansion, so every thread forms the same groups.)
+                unsigned tot = min(s_cnt[b], (unsigned)P.capPair);
+                int e = b + 1;
+                while (e < P.nb && tot + min(s_cnt[e], (unsigned)P.capPair) <= (unsigned)kGroupPairs) { tot += min(s_cnt[e], (unsigned)P.capPair); e++; }
+                if (tot == 0) { b = e; continue; }
+                const bool multi = e - b > 1;
+                for (int bb = b; bb < e; bb++)
+                    accumulate(pair_id + (long long)bb * P.capPair, pair_val + (long long)bb * P.capPair, min(s_cnt[bb], (unsigned)P.capPair), P.max_probe);
+                __syncthreads();
+                // settle: every thread scans its slots; reserve += coef * r (graph.h:90 / :106) goes to the log of the node's
+                // bucket (one counter update per warp and bucket), the push decision comes from the degree code in the key
+#pragma unroll 2
+                for (int j = 0; j < SPT / 2; j++) {
+                    const int slot = 2 * (j * BB + tid);
+                    const double2 r2 = *reinterpret_cast<const double2 *>(s_vals + slot);
+                    const double rr[2] = {r2.x, r2.y};
+                    const bool got[2] = {r2.x != 0.0, r2.y != 0.0};
+                    const unsigned m0 = __ballot_sync(0xffffffffu, got[0]), m1 = __ballot_sync(0xffffffffu, got[1]);
+                    if (m0 | m1) {   // (warp-uniform)
+                        const int2 k2 = *reinterpret_cast<const int2 *>(s_keys + slot);
+                        const unsigned key[2] = {(unsigned)k2.x, (unsigned)k2.y};
+                        if (got[0] | got[1]) *reinterpret_cast<double2 *>(s_vals + slot) = make_double2(0.0, 0.0);
+                        unsigned lb[2] = {(unsigned)b, (unsigned)b}, pos[2];
+                        if (!multi) {
+                            // one counter update per warp: the first slots of all lanes, then the second slots
+                            unsigned base = 0;
+                            if (lane == 0) base = atomicAdd(&s_lcnt[b], (unsigned)(__popc(m0) + __popc(m1)));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            const unsigned lt = (1u << lane) - 1u;
+                            pos[0] = base + __popc(m0 & lt);
+                            pos[1] = base + __popc(m0) + __popc(m1 & lt);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 2; q++) {
+                                lb[q] = got[q] ? hash_node(key[q] & idmask) >> bshift : 0xFFFFFFFFu;
+                                const unsigned peers = __match_any_sync(0xffffffffu, lb[q]);
+                                const int leader = __ffs(peers) - 1;
+                                unsigned p0 = 0;
+                                if (got[q] && lane == leader) p0 = atomicAdd(&s_lcnt[lb[q]], (unsigned)__popc(peers));
+                                pos[q] = __shfl_sync(0xffffffffu, p0, leader) + __popc(peers & ((1u << lane) - 1u));
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            if (got[q]) {
+                                src_front++;
+                                if (pos[q] < (unsigned)P.capLog) { log_id[(long long)lb[q] * P.capLog + pos[q]] = (int)key[q]; log_val[(long long)lb[q] * P.capLog + pos[q]] = c * rr[q]; }
+                                else ovf = true;
+                                if (will_push) {
+                                    const unsigned code = has_code ? key[q] >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
+                                    if (rr[q] >= P.rmax * (double)code) {                       // necessary for graph.h:94; the exact test follows
+                                        const int p = atomicAdd(&sm.n_sel, 1);
+                                        if (p < kCandCap) { sm.cand.key[p] = key[q]; sm.cand.r[p] = rr[q]; }
+                                        else consider(key[q], rr[q]);
+                                    }
+                                }
+                            }
+                        }
+                        *reinterpret_cast<int2 *>(s_keys + slot) = make_int2(kEmpty, kEmpty);   // the table is empty again for the next visit
+                    }
+                }
+                __syncthreads();
+                if (tid < e - b) s_cnt[b + tid] = 0;
+                if (tid == 0) sm.full = 0;
+                b = e;
+            }
+            __syncthreads();
+            if (will_push) {
+                const int n_sel = min(sm.n_sel, kCandCap);
+                for (int i = tid; i < n_sel; i += BB) consider(sm.cand.key[i], sm.cand.r[i]);
+            }
+            __syncthreads();
+            GPB_PHASE(2);
+        }
+        if (ovf) sm.ovf = 1;
+        __syncthreads();
+        const bool redo = sm.ovf != 0;
+        // ------------------------------------------------------------------ reserve: merge the logs bucket by bucket
+        if (tid == 0) sm.n_sup = 0;
+        __syncthreads();
+        long long m1x = 0;   // largest reserve this thread produced (non-negative doubles order like their bit patterns)
+        unsigned src_support = 0;
+        for (int b = 0; b < P.nb;) {
+            unsigned tot = min(s_lcnt[b], (unsigned)P.capLog);
+            int e = b + 1;
+            while (e < P.nb && tot + min(s_lcnt[e], (unsigned)P.capLog) <= (unsigned)kGroupPairs) { tot += min(s_lcnt[e], (unsigned)P.capLog); e++; }
+            if (tot != 0 && !redo) {
+                // (the table held these nodes at every level, or they are fewer than kGroupPairs: it cannot overflow)
+                for (int bb = b; bb < e; bb++)
+                    accumulate(log_id + (long long)bb * P.capLog, log_val + (long long)bb * P.capLog, min(s_lcnt[bb], (unsigned)P.capLog), kBuckets4);
+                __syncthreads();
+                // every claimed slot is one node of the support (its reserve may be exactly 0.0 in `single` mode)
+#pragma unroll 2
+                for (int j = 0; j < SPT / 2; j++) {
+                    const int slot = 2 * (j * BB + tid);
+                    const int2 k2 = *reinterpret_cast<const int2 *>(s_keys + slot);
+                    const bool got0 = k2.x != kEmpty, got1 = k2.y != kEmpty;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, got0), m1 = __ballot_sync(0xffffffffu, got1);
+                    if (m0 | m1) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&sm.n_sup, __popc(m0) + __popc(m1));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (got0 | got1) {
+                            const double2 x2 = *reinterpret_cast<const double2 *>(s_vals + slot);
+                            const unsigned lt = (1u << lane) - 1u;
+                            const long long p0 = base + __popc(m0 & lt), p1 = base + __popc(m0) + __popc(m1 & lt);
+                            if (got0) {
+                                if (p0 < P.capS) { sup_id[p0] = (int)((unsigned)k2.x & idmask); sup_val[p0] = x2.x; }
+                                src_support++;
+                                m1x = max(m1x, __double_as_longlong(x2.x));
+                            }
+                            if (got1) {
+                                if (p1 < P.capS) { sup_id[p1] = (int)((unsigned)k2.y & idmask); sup_val[p1] = x2.y; }
+                                src_support++;
+                                m1x = max(m1x, __double_as_longlong(x2.y));
+                            }
+                            *reinterpret_cast<double2 *>(s_vals + slot) = make_double2(0.0, 0.0);
+                            *reinterpret_cast<int2 *>(s_keys + slot) = make_int2(kEmpty, kEmpty);
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (tid < e - b) s_lcnt[b + tid] = 0;
+            b = e;
+        }
+        __syncthreads();
+        GPB_PHASE(3);
+        // ------------------------------------------------------------------ top-k, graph.h:111-126
+        const int n_sup = (int)min((long long)sm.n_sup, P.capS);
+        if (!redo) {
+            st_frontier += src_front; st_edges += src_edges;
+            st_support += src_support;
+            if (tid == 0) atomicMax(P.max_support, (unsigned long long)n_sup);
+            // Threshold: the K-th largest of the threads' maxima -- every thread's maximum is a distinct node's reserve, so at
+            // least K reserves are >= tau and nothing below tau can be among the K largest (K <= threads).  Found with the
+            // same radix select (one item per thread); the minimum of its winners is tau.
+            if (tid == 0) sm.tau_bits = 0x7fffffffffffffffll;
+            auto each_max = [&](auto f) { if (m1x > 0) f(__longlong_as_double(m1x), 0); };
+            const int n_max = block_topk<BB>(sm, P.K, false, each_max, [&](int, int, double v) { atomicMin(&sm.tau_bits, __double_as_longlong(v)); });
+            const double tau = n_max >= P.K ? __longlong_as_double(sm.tau_bits) : 0.0;
+            if (tid == 0) sm.n_list = 0;
+            __syncthreads();
+            bool listed = tau > 0.0;
+            if (listed) {
+                for (int j0 = tid; j0 < n_sup; j0 += 4 * BB) {
+                    double x[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) x[q] = j0 + q * BB < n_sup ? sup_val[j0 + q * BB] : 0.0;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (x[q] >= tau) {
+                            const int pos = atomicAdd(&sm.n_list, 1);
+                            if (pos < BB) { sm.add[pos] = x[q]; sm.start[pos] = sup_id[j0 + q * BB]; }
+                        }
+                    }
+                }
+                __syncthreads();
+                listed = sm.n_list <= BB;
+            }
+            const int n_list = listed ? sm.n_list : 0;
+            auto each = [&](auto f) {
+                if (listed) {
+                    for (int i = tid; i < n_list; i += BB) f(sm.add[i], sm.start[i]);
+                } else {
+                    for (int j = tid; j < n_sup; j += BB) {
+                        const double x = sup_val[j];
+                        if (x > 0.0) f(x, sup_id[j]);
+                    }
+                }
+            };
+            const int n = block_topk<BB>(sm, P.K, listed && n_list <= kBucketCap, each, [&](int pos, int id, double v) {
+                const long long o = it * P.K + pos;
+                P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
+                if (P.out_val32) P.out_val32[o] = (float)v;
+            });
+            // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
+            for (int i = n + tid; i < P.K; i += BB) {
+                const long long o = it * P.K + i;
+                P.out_row[o] = 0; P.out_col[o] = 0; P.out_val[o] = 0.0;
+                if (P.out_val32) P.out_val32[o] = 0.f;
+            }
+        } else if (tid == 0) {
+            P.redo[atomicAdd(P.redo_count, 1ull)] = (int)it; st_redo++; st_sources--;
+        }
+        if (tid == 0) { sm.ovf = 0; sm.full = 0; sm.n_push = 0; sm.n_sel = 0; }
+        GPB_PHASE(4);
+    }
+    // counters
+    for (int o = 16; o >= 1; o >>= 1) { st_frontier += __shfl_xor_sync(0xffffffffu, st_frontier, o); st_support += __shfl_xor_sync(0xffffffffu, st_support, o); }
+    if (lane == 0) {
+        if (st_support) { atomicAdd(P.stats + 2, st_support); atomicAdd(P.cum + 2, st_support); }
+        if (st_edges) { atomicAdd(P.stats + 0, st_edges); atomicAdd(P.cum + 0, st_edges); }
+        if (st_frontier) { atomicAdd(P.stats + 1, st_frontier); atomicAdd(P.cum + 1, st_frontier); }
+    }
+    if (tid == 0) {
+        sm.ph[7] = clock64() - t_begin;
+        for (int i = 0; i < 8; i++) atomicAdd(P.phase + i, (unsigned long long)sm.ph[i]);
+        atomicAdd(P.cum + 3, st_sources);
+        atomicAdd(P.cum + 4, st_sources);   // "cluster_sources": sources finished by the first-pass kernel
+        atomicAdd(P.cum + 5, st_redo);
+    }
+}
+#undef GPB_PHASE
+
+}  // namespace
+
+size_t gpb_dynamic_smem(int nb) { return (size_t)kSlots * 12 + (size_t)nb * 8; }
+
+int gpb_launch(const BucketPushParams &P, int ctas, cudaStream_t stream) {
+    static size_t configured = 0;
+    const size_t smem = gpb_dynamic_smem(P.nb);
+    if (smem > configured) {
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    gfpush_bucket_kernel<<<(unsigned)ctas, BB, smem, stream>>>(P);
+    GP_CUDA_TRY(cudaGetLastError());
+    return GP_OK;
+}
+
+}  // namespace gpp

@@ -47,7 +47,6 @@ constexpr int kBigCap = 32;
 constexpr int kItemBatch = 2;    // push-list entries a warp expands together
 constexpr int kChunk = 128;      // edges per push-list entry (longer entries are cut when they are appended)
 constexpr int kCandCap = 1024;   // nodes per level (and CTA) whose degree code allows a push; more are handled inline
-constexpr int kRankCap = 64;     // the radix select refines until the boundary bucket is this small, then rank-counts it
 
 struct CSmem {
     unsigned off[CB + 1];      // exclusive scan of the tile's degrees, off[CB] = total
@@ -117,82 +116,6 @@ __device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int
         }
     }
     return -1;
-}
-
-// The K largest of the items `each` enumerates (each(f) calls f(value > 0, id) for the calling thread's items; it is
-// invoked once per radix pass).  emit_fn(position, id, value) receives them in arbitrary order; returns their number.
-// MSD radix select on the fp64 bit pattern as in gfpush.cu.  Every thread of the CTA must call it.
-template <class Each, class Emit>
-__device__ __forceinline__ int block_topk(CSmem &sm, const int K, const bool small, Each each, Emit emit_fn) {
-    const int tid = threadIdx.x;
-    if (tid == 0) { sm.n_out = 0; sm.n_bucket = 0; }
-    int want_bucket = K;
-    if (small) {
-        // at most kBucketCap items in all (uniform): rank-count them directly
-        __syncthreads();
-        each([&](double x, int id) {
-            const int pos = atomicAdd(&sm.n_bucket, 1);
-            sm.sel.bkey[pos] = (unsigned long long)__double_as_longlong(x); sm.sel.bid[pos] = id;
-        });
-    } else {
-        for (int i = tid; i < kHistBins; i += CB) sm.sel.hist[i] = 0;
-        __syncthreads();
-        each([&](double x, int) { atomicAdd(&sm.sel.hist[(unsigned)((unsigned long long)__double_as_longlong(x) >> 52)], 1u); });
-        __syncthreads();
-        int shift = 52, bits = 11;
-        unsigned long long prefix = 0;   // value of key >> (shift + bits) shared by the boundary bucket
-        int kk = K;
-        bool first = true;
-        unsigned long long Tkey = 0;
-        for (;;) {
-            const unsigned total = select_bin_generic<CB>(sm.sel.hist, sm.warp_scan, 1 << bits, kk, first, &sm.sel_bin,
-                                                          &sm.sel_above, &sm.sel_inbin);
-            if (first) kk = min(kk, (int)total);   // k = min(K, #positive): graph.h:113 + the v > 0 filter of :121
-            if (kk == 0) { want_bucket = 0; Tkey = ~0ull; break; }
-            const int bin = sm.sel_bin, above = sm.sel_above, inbin = sm.sel_inbin;
-            Tkey = (prefix << bits) | (unsigned long long)bin;
-            want_bucket = kk - above;
-            if (inbin <= kRankCap || shift == 0) break;
-            kk = want_bucket; first = false; prefix = Tkey;
-            __syncthreads();
-            for (int i = tid; i < kHistBins; i += CB) sm.sel.hist[i] = 0;
-            __syncthreads();
-            const int nshift = shift >= 11 ? shift - 11 : 0;
-            const int nbits = shift >= 11 ? 11 : shift;
-            each([&](double x, int) {
-                const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-                if ((key >> shift) == prefix) atomicAdd(&sm.sel.hist[(unsigned)((key >> nshift) & ((1ull << nbits) - 1ull))], 1u);
-            });
-            shift = nshift; bits = nbits;
-            __syncthreads();
-        }
-        each([&](double x, int id) {
-            const unsigned long long key = (unsigned long long)__double_as_longlong(x);
-            const unsigned long long t = key >> shift;
-            if (t > Tkey) {
-                emit_fn(atomicAdd(&sm.n_out, 1), id, x);
-            } else if (t == Tkey) {
-                const int pos = atomicAdd(&sm.n_bucket, 1);
-                if (pos < kBucketCap) { sm.sel.bkey[pos] = key; sm.sel.bid[pos] = id; }
-            }
-        });
-    }
-    __syncthreads();
-    {
-        // rank-count the boundary bucket: keep its `want_bucket` largest (ties: lower position first)
-        const int nb = min(sm.n_bucket, kBucketCap);
-        for (int i = tid; i < nb; i += CB) {
-            const unsigned long long ki = sm.sel.bkey[i];
-            int rank = 0;
-            for (int q = 0; q < nb; q++) {
-                const unsigned long long kq = sm.sel.bkey[q];
-                rank += (kq > ki) || (kq == ki && q < i);
-            }
-            if (rank < want_bucket) emit_fn(atomicAdd(&sm.n_out, 1), sm.sel.bid[i], __longlong_as_double((long long)ki));
-        }
-    }
-    __syncthreads();
-    return sm.n_out;
 }
 
 template <int G>
@@ -658,8 +581,8 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
             double *cand_val = P.cand_val + cta * P.K;
             auto emit_cand = [&](int pos, int id, double v) { cand_id[pos] = id; cand_val[pos] = v; };
             int n;
-            if (G == 1) n = listed ? block_topk(sm, P.K, n_list <= kBucketCap, each_list, emit_out) : block_topk(sm, P.K, false, each_reg, emit_out);
-            else n = listed ? block_topk(sm, P.K, n_list <= kBucketCap, each_list, emit_cand) : block_topk(sm, P.K, false, each_reg, emit_cand);
+            if (G == 1) n = listed ? block_topk<CB>(sm, P.K, n_list <= kBucketCap, each_list, emit_out) : block_topk<CB>(sm, P.K, false, each_reg, emit_out);
+            else n = listed ? block_topk<CB>(sm, P.K, n_list <= kBucketCap, each_list, emit_cand) : block_topk<CB>(sm, P.K, false, each_reg, emit_cand);
             if (G == 1) {
                 // unfilled slots read (0, 0, 0.0): what graph.h:117-126 leaves in the caller-zeroed arrays
                 for (int i = n + tid; i < P.K; i += CB) {
@@ -703,7 +626,7 @@ __global__ void __launch_bounds__(CB, 1) gfpush_cluster_kernel(const ClusterPush
                             f(__ldcg(P.cand_val + a), __ldcg(P.cand_id + a));
                         }
                     };
-                    const int n = block_topk(sm, P.K, total <= (unsigned)kBucketCap, each_cand, [&](int pos, int id, double v) {
+                    const int n = block_topk<CB>(sm, P.K, total <= (unsigned)kBucketCap, each_cand, [&](int pos, int id, double v) {
                         const long long o = it * P.K + pos;
                         P.out_row[o] = src; P.out_col[o] = id; P.out_val[o] = v;
                         if (P.out_val32) P.out_val32[o] = (float)v;

@@ -109,6 +109,8 @@ typedef struct {
     int64_t redo_sources;    /* cumulative stats only: sources it handed over to the slab kernel       */
     int32_t cluster_size;    /* CTAs per source of the cluster kernel (0 = per-CTA kernels only)       */
     int32_t table_slots;     /* shared-memory residue-table slots per CTA (0 = residues on the HBM slabs)  */
+    int32_t bucket_count;    /* node-range buckets of the bucket kernel (0 = not used)                     */
+    int32_t reserved;
 } gp_push_stats;
 int gp_gfpush_last_stats(gp_graph *g, gp_push_stats *out);
 /* Counters summed over every gfpush since creation / the last reset (device-wide synchronise);
@@ -230,7 +232,7 @@ int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, 
  * 0 off, 1 auto from rmax, 2 always), "push_smem_probe" (4-key buckets tried before a node goes to the slab), "push_max_ctas"
  * (cap on persistent CTAs, for scaling experiments); the opt-in cluster kernel (one source per thread-block cluster):
  * "push_cluster" (0 off, 1 auto, -1 = one CTA, 2, 4, 8, 16 CTAs per source), "push_cluster_probe", "push_hub_deg",
- * "push_max_clusters".  The same keys are read from the GP_TUNING environment variable ("key=value,key=value") by the
+ * "push_max_clusters"; "push_bucket" (the hash-bucket kernel: 0 off, 1 auto, 2 always), "push_bucket_nb" (buckets per source, 0 = automatic).  The same keys are read from the GP_TUNING environment variable ("key=value,key=value") by the
  * Python loader. */
 int gp_set_tuning(const char *key, int64_t value);
 

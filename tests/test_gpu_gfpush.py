@@ -201,7 +201,7 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
-    DEFAULTS = {"push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+    DEFAULTS = {"push_bucket": 1, "push_bucket_nb": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
                 "push_smem_probe": 2, "push_max_ctas": 0}
 
     def __init__(self, **kv):
@@ -223,7 +223,9 @@ class _tuning:
 # CTA per source and with clusters of 2..16 CTAs exchanging pushed edges through L2, with hub entries shared by the
 # whole cluster, and with a probe limit so small that many sources are handed over to the slab kernel.
 TIERS = {
-    "slab": dict(push_cluster=0, push_smem_hash=0),
+    "slab": dict(push_cluster=0, push_smem_hash=0, push_bucket=0),
+    "bucket": dict(push_cluster=0, push_smem_hash=0, push_bucket=1),       # auto: takes the slab kernel's place
+    "bucket_forced": dict(push_cluster=0, push_bucket=2),
     "smem": dict(push_cluster=0, push_smem_hash=2),
     "smem_probe1": dict(push_cluster=0, push_smem_hash=2, push_smem_probe=1),
     "smem_probe2": dict(push_cluster=0, push_smem_hash=2, push_smem_probe=2),
@@ -264,7 +266,9 @@ def test_gfpush_tiers_give_the_oracle_rows_and_counters(tier):
     assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
     assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
     assert st["sources"] == len(src)
-    if kv.get("push_cluster") == 0:
+    if "bucket" in tier:
+        assert st["cluster_sources"] == len(src) and st["redo_sources"] == 0, st
+    elif kv.get("push_cluster") == 0:
         assert st["cluster_sources"] == 0 and st["redo_sources"] == 0
     else:
         assert st["cluster_sources"] + st["redo_sources"] == len(src)
@@ -295,6 +299,75 @@ def test_gfpush_smem_hash_matches_reference_golden(name, mode, probe):
         row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
     worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
     assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("cora", "single"), ("citeseer", "avg"), ("pubmed", "ppr"), ("pubmed", "single")])
+def test_gfpush_bucket_kernel_matches_reference_golden(name, mode):
+    """Real graphs through the hash-bucket kernel (forced: these supports fit the shared-memory table of the default path)."""
+    indptr, indices = load_graph(name)
+    z = np.load(os.path.join(GOLDEN, f"gfpush_{name}_{mode}.npz"))
+    K, rmax = int(z["K"]), float(z["rmax"])
+    with _tuning(push_bucket=2, push_cluster=0):
+        g = _graph(indptr, indices, scratch_mode=HBM)
+        g.cumulative_stats(reset=True)
+        row, col, val = _run(g, z["node_idx"].astype(np.int64), z["coef"], rmax, K)
+        st = g.cumulative_stats()
+        nb = g.last_stats()["bucket_count"]
+        assert nb >= 2 and nb & (nb - 1) == 0          # hash buckets: a power of two
+    assert st["cluster_sources"] == len(z["node_idx"]) and st["redo_sources"] == 0
+    worst = check_topk_rows(indptr, indices, z["node_idx"], z["coef"], rmax, K, col, val, row=row)
+    assert worst < 1e-11, worst
+    _, _, _, ost = og.gfpush(indptr, indices, z["node_idx"], z["coef"], rmax, K)
+    assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * max(ost.edges_pushed, 1)
+    assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
+    assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
+
+
+def test_gfpush_bucket_kernel_pilot_sizes_the_buckets():
+    """The first large call on a handle runs two sources per SM as a pilot, reads the largest support back and sizes the hash
+    buckets of the rest (and of later calls) from it; both parts write the same rows the oracle computes."""
+    indptr, indices = load_graph("pubmed")
+    n = indptr.shape[0] - 1
+    z = np.load(os.path.join(GOLDEN, "gfpush_pubmed_ppr.npz"))
+    K, rmax, coef = int(z["K"]), float(z["rmax"]), z["coef"]
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, n, 3000).astype(np.int64)
+    with _tuning(push_bucket=2, push_cluster=0):
+        g = _graph(indptr, indices, scratch_mode=HBM)
+        g.cumulative_stats(reset=True)
+        row, col, val = _run(g, src, coef, rmax, K)
+        st, last = g.cumulative_stats(), g.last_stats()
+        assert last["kernel_launches"] == 3                       # pilot + the rest + the (empty) slab pass
+        assert st["cluster_sources"] == len(src) and st["redo_sources"] == 0
+        nb_first = last["bucket_count"]
+        row2, col2, val2 = _run(g, src[:2500], coef, rmax, K)
+        last2 = g.last_stats()
+        assert last2["kernel_launches"] == 2 and last2["bucket_count"] == nb_first   # the measurement is kept on the handle
+    check_topk_rows(indptr, indices, src, coef, rmax, K, col, val, row=row, max_rows=96)
+    pick = np.r_[0:40, 280:320, 2960:3000]                        # pilot sources, the seam, the tail
+    check_topk_rows(indptr, indices, src[pick], coef, rmax, K, col.reshape(-1, K)[pick].ravel(), val.reshape(-1, K)[pick].ravel(),
+                    row=row.reshape(-1, K)[pick].ravel())
+    # (the order of the slots within a row is not defined, and fp64 sums depend on the order the pairs arrive in)
+    np.testing.assert_allclose(np.sort(val.reshape(-1, K)[:2500], axis=1), np.sort(val2.reshape(-1, K), axis=1), rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("name", ["path8", "star33", "isolated", "dangling"])
+def test_gfpush_bucket_kernel_tiny_graphs(name):
+    """Dangling nodes, K > support, degree-1 nodes, zero-valued reserves (`single`): graph.h:91-93,113,121 on the bucket kernel."""
+    z = np.load(os.path.join(GOLDEN, f"tiny_{name}.npz"))
+    reps = 6
+    src = np.tile(z["node_idx"], reps)
+    with _tuning(push_bucket=2, push_cluster=0):
+        g = _graph(z["indptr"], z["indices"], scratch_mode=HBM)
+        for tag in sorted({k.split("/")[0] for k in z.files if "/" in k}):
+            K, rmax, coef = int(z[f"{tag}/K"]), float(z[f"{tag}/rmax"]), z[f"{tag}/coef"]
+            g.cumulative_stats(reset=True)
+            row, col, val = _run(g, src, coef, rmax, K)
+            st = g.cumulative_stats()
+            assert st["cluster_sources"] == len(src), (tag, st)
+            check_topk_rows(z["indptr"], z["indices"], src, coef, rmax, K, col, val, row=row)
+            ref_filled = np.tile((z[f"{tag}/value"].reshape(-1, K) > 0).sum(1), reps)
+            np.testing.assert_array_equal((val.reshape(-1, K) > 0).sum(1), ref_filled)
 
 
 @pytest.mark.parametrize("name,mode", [("cora", "ppr"), ("citeseer", "avg"), ("pubmed", "ppr"), ("pubmed", "single")])

@@ -12,9 +12,9 @@ coef = og.coef_for("ppr", 5, 0.1)
 """Small GFPush run for compute-sanitizer (memcheck / racecheck) over every residue-table mode:
     compute-sanitizer --tool racecheck python tools/sanitize_gfpush.py"""
 for kv in (dict(push_cluster=0, push_smem_hash=2, push_smem_probe=4), dict(push_cluster=0, push_smem_hash=2, push_smem_probe=1),
-           dict(push_cluster=0, push_smem_hash=0), dict(scratch=1),
+           dict(push_cluster=0, push_smem_hash=0, push_bucket=0), dict(scratch=1),
            dict(push_cluster=-1), dict(push_cluster=2), dict(push_cluster=4, push_hub_deg=8), dict(push_cluster=16),
-           dict(push_cluster=2, push_cluster_probe=1)):
+           dict(push_cluster=2, push_cluster_probe=1), dict(push_cluster=0, push_bucket=2)):
     scratch = kv.pop("scratch", 2)
     for k, v in kv.items(): _lib.set_tuning(k, v)
     g = propagation.Graph(indptr, indices, 0); g.configure(scratch_mode=scratch)

@@ -16,7 +16,7 @@ import bench  # noqa: E402
 from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
-DEFAULTS = {"push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+DEFAULTS = {"push_bucket": 1, "push_bucket_nb": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
             "push_smem_probe": 2, "push_max_ctas": 0}
 
 
@@ -66,7 +66,7 @@ def main():
         st = graph.cumulative_stats(reset=True)
         ls = graph.last_stats()
         print(f"{name} S={S} {cfg:44s} rows/s={S * steps / t:12.0f}  edges/s={st['edges_pushed'] / t / 1e9:7.2f}G  "
-              f"G={ls['cluster_size']} ctas={ls['ctas']} cluster={st['cluster_sources']} redo={st['redo_sources']} "
+              f"G={ls['cluster_size']} nb={ls['bucket_count']} ctas={ls['ctas']} cluster={st['cluster_sources']} redo={st['redo_sources']} "
               f"sup/src={st['support_total'] / max(st['sources'], 1):.0f} scratch={ls['scratch_bytes'] / 1e6:.0f}MB "
               f"[E={st['edges_pushed']} F={st['frontier_total']} S={st['support_total']}]", flush=True)
         ph = graph.phase_cycles(reset=True)
