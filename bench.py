@@ -276,12 +276,13 @@ def measure_workload(name, dev, rank, world, steps, warmup, sources=0, configure
         sm_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
     except Exception:
         pass
-    kernel = "gfpush_cluster_kernel" if last.get("cluster_size", 0) > 0 else "gfpush_kernel"
+    kernel = ("gfpush_cluster_kernel" if last.get("cluster_size", 0) > 0 else
+              "gfpush_bucket_kernel" if last.get("bucket_count", 0) > 0 else "gfpush_kernel")
     edges_per_s = stats["edges_pushed"] / t_push
     resident = max(phases.get("resident", 0), 1)
     roof_push = {"kernel": kernel, "bound": "hbm", "achieved": push_bytes / t_push / 1e9, "peak": peak,
                  "unit": "GB/s", "frac": push_bytes / t_push / 1e9 / peak,
-                 "traffic": load_traffic(name, "gfpush_kernel"), "peak_source": peak_src,
+                 "traffic": load_traffic(name, kernel), "peak_source": peak_src,
                  "ms_per_launch": t_push / steps * 1e3, "share_of_step": t_push / t_dev,
                  "edges_per_s": edges_per_s, "edges_per_source": stats["edges_pushed"] / (S * steps),
                  "algorithmic_bytes_per_launch": push_bytes / steps,
@@ -294,7 +295,7 @@ def measure_workload(name, dev, rank, world, steps, warmup, sources=0, configure
                  # box-to-box differences (gp_gfpush_phase_cycles)
                  "phase_share": {k: v / resident for k, v in phases.items() if k != "resident"},
                  "cta_us_per_source": phases.get("resident", 0) / sm_mhz / max(stats["sources"], 1),
-                 "table_slots": last.get("table_slots", 0),
+                 "table_slots": last.get("table_slots", 0), "bucket_count": last.get("bucket_count", 0),
                  "second_roof": second_roof(last, edges_per_s, props.multi_processor_count, sm_mhz)}
     roof_agg = {"kernel": "aggregate_fwd_kernel", "bound": "hbm", "achieved": agg_bytes / t_agg / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": agg_bytes / t_agg / 1e9 / peak,
