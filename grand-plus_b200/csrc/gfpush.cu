@@ -54,6 +54,7 @@ int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree
 int g_push_bucket = 1;        // "push_bucket": the hash-bucket kernel (gfpush_bucket.cu) for supports far beyond shared memory:
                               // 0 off, 1 auto (where the slab kernel would run), 2 always
 int g_push_bucket_nb = 0;     // "push_bucket_nb": buckets per source (rounded up to a power of two); 0 = from the expected support
+int g_push_bucket_merge = 0;  // "push_bucket_merge": 0 = merge only the top-k candidates (the support is not counted), 1 = merge the whole reserve
 int g_push_max_clusters = 0;  // "push_max_clusters": cap on the resident clusters (0 = all the device schedules); scaling experiments
 int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments
 int g_push_tuning_gen = 0;    // bumped by gp_set_tuning so that handles re-plan
@@ -1123,15 +1124,16 @@ void plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, l
     long long capE = g->nnz + n;
     if (rmax > 0.0) capE = (long long)std::min<double>((double)capE, std::ceil(1.0 / rmax * 1.0001) + 16.0);
     // buckets: a power of two >= 2 such that the LARGEST support seen on this handle for these parameters (a pilot launch
-    // measures it, push_device_locked) loads the table to <= 0.8; without a measurement the a-priori bound min(n, 1.5 x the
+    // measures it, push_device_locked) loads the table to <= 0.9; without a measurement the a-priori bound min(n, 1.5 x the
     // per-level edge bound) stands in, which is several times too large on the BASELINE shapes: more and smaller visits
     // than necessary, but never an overflow.  A source that outgrows the table anyway is handed to the slab kernel.
     long long nb = 2;
     if (g_push_bucket_nb > 0) {
         while (nb < g_push_bucket_nb && nb < kBucketMaxBuckets) nb *= 2;
     } else {
-        const long long est = support_hint > 0 ? support_hint + support_hint / 16 : std::min<long long>(n, capE + capE / 2);
-        while (nb < kBucketMaxBuckets && est > nb * (kBucketSlots * 4ll / 5)) nb *= 2;
+        // (the probe sequence only runs out near a load of 1: the largest support seen may load the table to 0.9)
+        if (support_hint > 0) while (nb < kBucketMaxBuckets && support_hint > nb * (kBucketSlots * 9ll / 10)) nb *= 2;
+        else while (nb < kBucketMaxBuckets && std::min<long long>(n, capE + capE / 2) > nb * (kBucketSlots * 4ll / 5)) nb *= 2;
     }
     int log_nb = 0;
     while ((1ll << log_nb) < nb) log_nb++;
@@ -1284,7 +1286,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             GP_CUDA_TRY(cudaMalloc(&g->d_redo, sizeof(int) * (size_t)S));
             g->d_redo_cap = (size_t)S;
         }
-        auto launch_bucket = [&](const BucketPlan &b, long long first, long long last) -> int {
+        auto launch_bucket = [&](const BucketPlan &b, long long first, long long last, bool full_merge) -> int {
             if (g->bscratch_bytes < b.bytes) {
                 GP_CUDA_TRY(cudaStreamSynchronize(stream));
                 if (g->ev_recorded) GP_CUDA_TRY(cudaEventSynchronize(g->ev_done));
@@ -1296,6 +1298,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             BucketPushParams B{};
             B.node_rec = g->d_node_rec; B.packed = g->d_packed; B.n = (int)g->n; B.idbits = g->idbits; B.nb = b.nb; B.log_nb = b.log_nb;
             B.max_probe = std::max(g_push_cluster_probe, 1);
+            B.full_merge = full_merge ? 1 : 0;
             B.node_idx = d_node_idx; B.S = last; B.it_base = first; B.coef = g->d_coef; B.L = L; B.rmax = rmax; B.K = K;
             B.out_row = d_row; B.out_col = d_col; B.out_val = d_val; B.out_val32 = d_val32;
             B.pair_id = (int *)(bb + b.off_pi); B.pair_val = (double *)(bb + b.off_pv); B.capPair = b.capPair;
@@ -1314,7 +1317,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             // Pilot: two sources per SM with the a-priori bucket count, then read the largest support back (the one
             // synchronisation of the first call on a handle) and size the buckets of the rest -- and of later calls -- from it.
             first = std::min<long long>(S, 2ll * g->num_sms);
-            rc = launch_bucket(bp, 0, first);
+            rc = launch_bucket(bp, 0, first, true);   // (the full merge counts the support)
             if (rc != GP_OK) return rc;
             unsigned long long h_max = 0;
             GP_CUDA_TRY(cudaMemcpyAsync(&h_max, g->d_ctrl + 8, sizeof h_max, cudaMemcpyDeviceToHost, stream));
@@ -1326,7 +1329,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long), stream));   // the queue restarts at `first`
         }
         if (first < S) {
-            rc = launch_bucket(bp, first, S);
+            rc = launch_bucket(bp, first, S, g_push_bucket_merge != 0);
             if (rc != GP_OK) return rc;
         }
         P.redo = g->d_redo; P.redo_count = g->d_ctrl + 6;

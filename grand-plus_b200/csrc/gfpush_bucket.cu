@@ -38,6 +38,7 @@ constexpr int kBigLen = 4096;           // longer entries stay whole and are exp
 constexpr int kBigCap = 32;
 constexpr int kItemBatch = 2;
 constexpr int kCandCap = 1024;
+constexpr int kCandMax = kSlots / 2;          // nodes the candidate merge can hold in one table fill
 constexpr int kGroupPairs = kSlots * 5 / 8;   // buckets are visited together while their pairs stay below this table load
 
 __device__ __forceinline__ unsigned hash_node(unsigned id) { return id * 2654435761u; }
@@ -63,6 +64,35 @@ __device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int
     return -1;
 }
 
+// The r-th largest of the lanes' values (bit patterns of non-negative doubles; 0 when fewer than r lanes hold a positive one).
+__device__ __forceinline__ long long warp_rth_largest(long long v, int r) {
+    const int lane = threadIdx.x & 31;
+    long long r_val = 0;
+    for (int i = 0; i < r; i++) {
+        long long mx = v;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        r_val = mx;
+        const unsigned holders = __ballot_sync(0xffffffffu, v == mx);
+        if (lane == __ffs(holders) - 1) v = 0;
+    }
+    return r_val;
+}
+
+// Slot of packed node `vp` if the table holds it, else -1 (never claims).
+__device__ __forceinline__ int lookup_slot(const int *keys, unsigned bucket, int vp) {
+    unsigned b = bucket;
+    for (int probe = 0; probe < kBuckets4; probe++, b = (b + 1) & (kBuckets4 - 1)) {
+        const int4 k4 = *reinterpret_cast<const int4 *>(keys + 4 * b);
+        if (k4.x == vp) return (int)(4 * b);
+        if (k4.y == vp) return (int)(4 * b + 1);
+        if (k4.z == vp) return (int)(4 * b + 2);
+        if (k4.w == vp) return (int)(4 * b + 3);
+        if (k4.w == kEmpty) return -1;   // (the used slots of a bucket are a prefix)
+    }
+    return -1;
+}
+
 struct BSmem {
     int start[BB];             // push list of the level: first BB entries {start, len, add}; during the top-k (the list is
                                // dead then) `add` / `start` hold the survivors of the pre-filter
@@ -82,7 +112,7 @@ struct BSmem {
         } cand;
     };
     long long it;
-    int n_push, n_sel, n_sup, n_list, next_item, n_big;
+    int n_push, n_sel, n_sup, n_all, n_list, next_item, n_big, n_cand;   // n_sup: reserves written out, n_all: nodes of the support
     int big_st[kBigCap];
     unsigned big_len[kBigCap];
     double big_add[kBigCap];
@@ -91,6 +121,7 @@ struct BSmem {
     int ovf;
     int full;                  // a probe sequence ran out: the source goes to the slab kernel, stop probing
     long long tau_bits;
+    double tau_lb;             // a lower bound of the source's K-th largest reserve, from the levels settled so far
     long long ph[8], t_prev;
 };
 
@@ -100,6 +131,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
     int *s_keys = reinterpret_cast<int *>(s_vals + kSlots);             // [kSlots] packed node, kEmpty = free
     unsigned *s_cnt = reinterpret_cast<unsigned *>(s_keys + kSlots);    // [nb] pairs per bucket (this level)
     unsigned *s_lcnt = s_cnt + P.nb;                                    // [nb] reserve-log entries per bucket (this source)
+    unsigned *s_lmark = s_lcnt + P.nb;                                  // [nb] ... before the current level (deferred candidates)
     const int bshift = 32 - P.log_nb;                                   // hash >> bshift = bucket (log_nb >= 1)
 
     const int tid = threadIdx.x;
@@ -117,6 +149,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
     int *sup_id = P.sup_id + cta * P.capS;
     double *sup_val = P.sup_val + cta * P.capS;
     unsigned long long *err = P.stats + 3;
+    const int capC = (int)min((long long)kCandMax, P.capS);   // the candidate list lives in sup_id until the merge
 
     for (int i = tid; i < kSlots; i += BB) { s_vals[i] = 0.0; s_keys[i] = kEmpty; }
     for (int i = tid; i < P.nb; i += BB) { s_cnt[i] = 0; s_lcnt[i] = 0; }
@@ -243,6 +276,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             log_id[(long long)b0 * P.capLog] = src_key; log_val[(long long)b0 * P.capLog] = P.coef[0];
             s_lcnt[b0] = 1;
             src_front++;
+            sup_id[0] = src_key; sm.n_cand = 1; sm.tau_lb = 0.0;   // candidate merge (below): the source is a candidate
         }
         __syncthreads();
         GPB_PHASE(0);
@@ -356,6 +390,17 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             const int nl = level + 1;
             const bool will_push = nl < P.L - 1;
             const double c = P.coef[nl];
+            // Candidate merge (see the merge below): a node can only be among the K largest if ONE of its <= L contributions
+            // coef * r is >= (K-th largest reserve) / L.  tau_lb is a lower bound of that reserve, so every contribution
+            // >= tau_lb / L notes its node as a candidate (while tau_lb is 0: every node).
+            const double cand_thr = sm.tau_lb / (double)P.L * (1.0 - 1e-9);
+            // A large level that arrives before any bound exists (a source with fewer than K neighbours whose neighbours have
+            // thousands) would note every node: its candidates are picked from its log entries AFTER the level has set tau_lb.
+            unsigned level_pairs = 0;
+            for (int b = 0; b < P.nb; b++) level_pairs += s_cnt[b];
+            const bool defer = !P.full_merge && sm.tau_lb == 0.0 && level_pairs > 2048u;
+            if (defer && tid < P.nb) s_lmark[tid] = min(s_lcnt[tid], (unsigned)P.capLog);
+            long long lvl_max = 0;   // this thread's largest contribution of the level (a node of its own: a level's nodes are distinct)
             for (int b = 0; b < P.nb;) {
                 // one visit = consecutive buckets [b, e) whose pairs together cannot overfill the table (pairs bound the
                 // distinct nodes); a bucket above the limit is a visit of its own.  (s_cnt is stable since the barrier that
@@ -405,8 +450,14 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                         for (int q = 0; q < 2; q++) {
                             if (got[q]) {
                                 src_front++;
-                                if (pos[q] < (unsigned)P.capLog) { log_id[(long long)lb[q] * P.capLog + pos[q]] = (int)key[q]; log_val[(long long)lb[q] * P.capLog + pos[q]] = c * rr[q]; }
+                                const double cr = c * rr[q];
+                                if (pos[q] < (unsigned)P.capLog) { log_id[(long long)lb[q] * P.capLog + pos[q]] = (int)key[q]; log_val[(long long)lb[q] * P.capLog + pos[q]] = cr; }
                                 else ovf = true;
+                                lvl_max = max(lvl_max, __double_as_longlong(cr));
+                                if (!defer && cr >= cand_thr) {   // (rare once the first two or three levels have set tau_lb)
+                                    const int p = atomicAdd(&sm.n_cand, 1);
+                                    if (p < capC) sup_id[p] = (int)key[q];
+                                }
                                 if (will_push) {
                                     const unsigned code = has_code ? key[q] >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
                                     if (rr[q] >= P.rmax * (double)code) {                       // necessary for graph.h:94; the exact test follows
@@ -431,16 +482,114 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                 for (int i = tid; i < n_sel; i += BB) consider(sm.cand.key[i], sm.cand.r[i]);
             }
             __syncthreads();
+            if (!P.full_merge && P.K <= BB) {
+                // tau_lb: the K-th largest of the threads' largest contributions of this level -- K different nodes whose
+                // reserve is at least that (a level's nodes are distinct, contributions only add up)
+                if (tid == 0) sm.tau_bits = 0x7fffffffffffffffll;
+                auto each_max = [&](auto f) { if (lvl_max > 0) f(__longlong_as_double(lvl_max), 0); };
+                const int n_max = block_topk<BB>(sm, P.K, false, each_max, [&](int, int, double v) { atomicMin(&sm.tau_bits, __double_as_longlong(v)); });
+                if (tid == 0 && n_max >= P.K) sm.tau_lb = fmax(sm.tau_lb, __longlong_as_double(sm.tau_bits));
+                __syncthreads();
+                if (defer) {   // this level's log entries (just written: L2) against the bound the level itself gave
+                    const double thr = sm.tau_lb / (double)P.L * (1.0 - 1e-9);
+                    for (int b = 0; b < P.nb; b++) {
+                        const unsigned hi = min(s_lcnt[b], (unsigned)P.capLog);
+                        for (unsigned i = s_lmark[b] + tid; i < hi; i += BB) {
+                            if (log_val[(long long)b * P.capLog + i] >= thr) {
+                                const int p = atomicAdd(&sm.n_cand, 1);
+                                if (p < capC) sup_id[p] = log_id[(long long)b * P.capLog + i];
+                            }
+                        }
+                    }
+                }
+            }
             GPB_PHASE(2);
         }
         if (ovf) sm.ovf = 1;
         __syncthreads();
         const bool redo = sm.ovf != 0;
         // ------------------------------------------------------------------ reserve: merge the logs bucket by bucket
-        if (tid == 0) sm.n_sup = 0;
+        // Only reserves that can still be among the K largest are written out: a running threshold tau_run with at least K
+        // reserves >= it.  Every warp publishes the r-th largest of its lanes' maxima, r = ceil(K / 32) (a lane's maximum is a
+        // node of its own, so the warp has seen r reserves >= that value); the minimum over the warps bounds K of them.  The
+        // published values only grow, so a reader that sees a mix of old and new ones still holds a valid (lower) bound.
+        const int rth = (P.K + 31) / 32;
+        if (tid == 0) {
+            sm.n_sup = 0; sm.n_all = 0;
+        }
+        if (lane == 0) sm.wtau[tid >> 5] = 0.0;
         __syncthreads();
         long long m1x = 0;   // largest reserve this thread produced (non-negative doubles order like their bit patterns)
         unsigned src_support = 0;
+        // Writes the table's nodes with a reserve >= tau_run to the compact arrays and empties the table.
+        auto drain = [&](const double tau_run) {
+#pragma unroll 2
+            for (int j = 0; j < SPT / 2; j++) {
+                const int slot = 2 * (j * BB + tid);
+                const int2 k2 = *reinterpret_cast<const int2 *>(s_keys + slot);
+                const bool got0 = k2.x != kEmpty, got1 = k2.y != kEmpty;
+                if (__any_sync(0xffffffffu, got0 | got1)) {
+                    double2 x2 = make_double2(0.0, 0.0);
+                    if (got0 | got1) {
+                        x2 = *reinterpret_cast<const double2 *>(s_vals + slot);
+                        *reinterpret_cast<double2 *>(s_vals + slot) = make_double2(0.0, 0.0);
+                        *reinterpret_cast<int2 *>(s_keys + slot) = make_int2(kEmpty, kEmpty);
+                    }
+                    const bool keep0 = got0 && x2.x >= tau_run, keep1 = got1 && x2.y >= tau_run;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, keep0), m1 = __ballot_sync(0xffffffffu, keep1);
+                    if (m0 | m1) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&sm.n_sup, __popc(m0) + __popc(m1));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        const unsigned lt = (1u << lane) - 1u;
+                        const long long p0 = base + __popc(m0 & lt), p1 = base + __popc(m0) + __popc(m1 & lt);
+                        if (keep0 && p0 < P.capS) { sup_id[p0] = (int)((unsigned)k2.x & idmask); sup_val[p0] = x2.x; }
+                        if (keep1 && p1 < P.capS) { sup_id[p1] = (int)((unsigned)k2.y & idmask); sup_val[p1] = x2.y; }
+                    }
+                    if (got0) { src_support++; m1x = max(m1x, __double_as_longlong(x2.x)); }
+                    if (got1) { src_support++; m1x = max(m1x, __double_as_longlong(x2.y)); }
+                }
+            }
+        };
+        // CANDIDATE MERGE (default).  The K largest reserves are wanted, not the whole reserve vector: only the candidates
+        // noted during the levels (a few hundred to a few thousand nodes against a support of 10^5) get a table slot, then
+        // the logs stream through ONCE with a read-only lookup per entry -- almost always a miss decided by one 16-byte
+        // shared-memory read, no claim, no add -- and one table scan writes the candidates' reserves out.  The support itself
+        // is never materialised (gp_push_stats.support_total does not count these sources).  Falls back to the full merge
+        // when the candidates outgrow half a table, when K > 1024, or when P.full_merge asks for the support count.
+        const bool cand_merge = !redo && !P.full_merge && P.K <= BB && sm.n_cand <= capC;
+        if (cand_merge) {
+            const int n_cand = sm.n_cand;
+            for (int i = tid; i < n_cand; i += BB) {
+                const int vp = sup_id[i];
+                bool claimed;
+                find_slot(s_keys, (hash_node((unsigned)vp & idmask) >> (bshift - 12)) & (kBuckets4 - 1), vp, kBuckets4, claimed);
+            }
+            __syncthreads();
+            for (int b = 0; b < P.nb; b++) {
+                const unsigned n = min(s_lcnt[b], (unsigned)P.capLog);
+                const int *lid = log_id + (long long)b * P.capLog;
+                const double *lval = log_val + (long long)b * P.capLog;
+                for (unsigned i0 = tid; i0 < n; i0 += BB * 4) {
+                    int vp[4], at[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) vp[q] = i0 + BB * q < n ? __ldcs(lid + i0 + BB * q) : kEmpty;
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        at[q] = -1;
+                        if (vp[q] != kEmpty) at[q] = lookup_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> (bshift - 12)) & (kBuckets4 - 1), vp[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+                        if (at[q] >= 0) atomicAdd(s_vals + at[q], __ldcs(lval + i0 + BB * q));   // (the value is only read for a candidate)
+                }
+            }
+            __syncthreads();
+            drain(0.0);
+            __syncthreads();
+            if (tid < P.nb) s_lcnt[tid] = 0;
+            src_support = 0;   // (candidates, not the support)
+        } else
         for (int b = 0; b < P.nb;) {
             unsigned tot = min(s_lcnt[b], (unsigned)P.capLog);
             int e = b + 1;
@@ -451,48 +600,31 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                     accumulate(log_id + (long long)bb * P.capLog, log_val + (long long)bb * P.capLog, min(s_lcnt[bb], (unsigned)P.capLog), kBuckets4);
                 __syncthreads();
                 // every claimed slot is one node of the support (its reserve may be exactly 0.0 in `single` mode)
-#pragma unroll 2
-                for (int j = 0; j < SPT / 2; j++) {
-                    const int slot = 2 * (j * BB + tid);
-                    const int2 k2 = *reinterpret_cast<const int2 *>(s_keys + slot);
-                    const bool got0 = k2.x != kEmpty, got1 = k2.y != kEmpty;
-                    const unsigned m0 = __ballot_sync(0xffffffffu, got0), m1 = __ballot_sync(0xffffffffu, got1);
-                    if (m0 | m1) {
-                        int base = 0;
-                        if (lane == 0) base = atomicAdd(&sm.n_sup, __popc(m0) + __popc(m1));
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        if (got0 | got1) {
-                            const double2 x2 = *reinterpret_cast<const double2 *>(s_vals + slot);
-                            const unsigned lt = (1u << lane) - 1u;
-                            const long long p0 = base + __popc(m0 & lt), p1 = base + __popc(m0) + __popc(m1 & lt);
-                            if (got0) {
-                                if (p0 < P.capS) { sup_id[p0] = (int)((unsigned)k2.x & idmask); sup_val[p0] = x2.x; }
-                                src_support++;
-                                m1x = max(m1x, __double_as_longlong(x2.x));
-                            }
-                            if (got1) {
-                                if (p1 < P.capS) { sup_id[p1] = (int)((unsigned)k2.y & idmask); sup_val[p1] = x2.y; }
-                                src_support++;
-                                m1x = max(m1x, __double_as_longlong(x2.y));
-                            }
-                            *reinterpret_cast<double2 *>(s_vals + slot) = make_double2(0.0, 0.0);
-                            *reinterpret_cast<int2 *>(s_keys + slot) = make_int2(kEmpty, kEmpty);
-                        }
-                    }
+                double tau_run = sm.wtau[0];
+#pragma unroll 8
+                for (int w = 1; w < BB / 32; w++) tau_run = fmin(tau_run, sm.wtau[w]);
+                drain(tau_run);
+                if (rth <= 32) {   // the warp's rth-largest lane maximum (0.0 while fewer than rth lanes hold a positive reserve)
+                    const long long r_val = warp_rth_largest(m1x, rth);
+                    if (lane == 0) sm.wtau[tid >> 5] = __longlong_as_double(r_val);
                 }
                 __syncthreads();
             }
             if (tid < e - b) s_lcnt[b + tid] = 0;
             b = e;
         }
+        {
+            const unsigned ws = __reduce_add_sync(0xffffffffu, src_support);
+            if (lane == 0 && ws) atomicAdd(&sm.n_all, (int)ws);
+        }
         __syncthreads();
+        if (tid == 0 && sm.n_all) atomicMax(P.max_support, (unsigned long long)sm.n_all);   // (full merge only: sizes the buckets of later calls)
         GPB_PHASE(3);
         // ------------------------------------------------------------------ top-k, graph.h:111-126
         const int n_sup = (int)min((long long)sm.n_sup, P.capS);
         if (!redo) {
             st_frontier += src_front; st_edges += src_edges;
             st_support += src_support;
-            if (tid == 0) atomicMax(P.max_support, (unsigned long long)n_sup);
             // Threshold: the K-th largest of the threads' maxima -- every thread's maximum is a distinct node's reserve, so at
             // least K reserves are >= tau and nothing below tau can be among the K largest (K <= threads).  Found with the
             // same radix select (one item per thread); the minimum of its winners is tau.
@@ -566,7 +698,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
 
 }  // namespace
 
-size_t gpb_dynamic_smem(int nb) { return (size_t)kSlots * 12 + (size_t)nb * 8; }
+size_t gpb_dynamic_smem(int nb) { return (size_t)kSlots * 12 + (size_t)nb * 12; }
 
 int gpb_launch(const BucketPushParams &P, int ctas, cudaStream_t stream) {
     static size_t configured = 0;

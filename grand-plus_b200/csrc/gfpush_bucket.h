@@ -16,6 +16,7 @@ struct BucketPushParams {
     int nb;                    // buckets = 2^log_nb (>= 2): bucket of a node = hash(node) >> (32 - log_nb)
     int log_nb;
     int max_probe;             // 4-key buckets of the table tried before the source is handed to the slab kernel
+    int full_merge;            // 1: merge the whole reserve (counts the support); 0: only the top-k candidates (default)
     const int *node_idx;
     long long S;               // sources [it_base, S) of node_idx are processed by this launch
     long long it_base;

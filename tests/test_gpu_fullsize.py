@@ -21,9 +21,10 @@ SHAPES = {
     "mag": (10_541_560, 265_219_994, 10, 0.2, 1e-5, 32, 2048, 2, 500_000),    # scripts/run_mag.sh:7
 }
 TIER_TUNING = {"cluster": dict(push_cluster=1, push_bucket=0), "table": dict(push_cluster=0, push_smem_hash=2, push_bucket=0),
-               "bucket": dict(push_cluster=0, push_smem_hash=0, push_bucket=2),
+               "bucket": dict(push_cluster=0, push_smem_hash=0, push_bucket=2, push_bucket_merge=1),
+               "bucket_cand": dict(push_cluster=0, push_smem_hash=0, push_bucket=2, push_bucket_merge=0),
                "slabs": dict(push_cluster=0, push_smem_hash=0, push_bucket=0)}
-TUNING_DEFAULTS = dict(push_cluster=0, push_smem_hash=1, push_bucket=1)
+TUNING_DEFAULTS = dict(push_cluster=0, push_smem_hash=1, push_bucket=1, push_bucket_merge=0)
 
 
 def _build(shape):
@@ -57,7 +58,7 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
     indptr, indices, graph, src = request.getfixturevalue("reddit_shape") if shape == "reddit" else _build(shape)
     coef = og.coef_for("ppr", order, alpha)
     # (the MAG-shape graph has 644 buckets with ~30 pushed edges each: the bucket kernel is correct there but is not its home)
-    tiers = {"reddit": ("cluster", "table", "bucket", "slabs"), "amazon2m": ("cluster", "bucket", "slabs"),
+    tiers = {"reddit": ("cluster", "table", "bucket", "bucket_cand", "slabs"), "amazon2m": ("cluster", "bucket", "bucket_cand", "slabs"),
              "mag": ("cluster", "table", "slabs")}[shape]
     out = {}
     try:
@@ -82,6 +83,9 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
         _, ca, va, sa, _ = out[tier]
         # work counters are integers of the algorithm: every kernel counts the same pushes, frontiers and supports
         for key in ("edges_pushed", "frontier_total", "support_total", "sources"):
+            if tier == "bucket_cand" and key == "support_total":
+                assert sa[key] <= 0.1 * sb[key]   # the candidate merge never materialises the support (hand-overs and fall-backs do)
+                continue
             assert abs(sa[key] - sb[key]) <= 1e-6 * sb[key], (tier, key, sa[key], sb[key])
         same = 0
         for (ac, av), (bc, bv) in zip(_rows(ca, va, k), rb):
@@ -97,11 +101,12 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
         assert float(sums.max()) <= 1.0 + 1e-12 and float(sums.min()) >= coef[0] * (1 - 1e-12)
     # the oracle itself on a sample of rows (hub source included), rows and work counters
     ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
-    sbk = out["bucket"][3] if "bucket" in out else None
-    if sbk is not None:
-        assert sbk["cluster_sources"] + sbk["redo_sources"] == len(src) and sbk["redo_sources"] <= 0.02 * len(src), sbk
-        nb = out["bucket"][4]["bucket_count"]
-        assert nb >= 2 and nb & (nb - 1) == 0
+    for bt in ("bucket", "bucket_cand"):
+        if bt in out:
+            sbk = out[bt][3]
+            assert sbk["cluster_sources"] + sbk["redo_sources"] == len(src) and sbk["redo_sources"] <= 0.02 * len(src), sbk
+            nb = out[bt][4]["bucket_count"]
+            assert nb >= 2 and nb & (nb - 1) == 0
     row, ca, va = out["cluster"][:3]
     worst = check_topk_rows(ip, ix, src.cpu().numpy(), coef, rmax, k, ca.cpu().numpy().reshape(-1),
                             va.cpu().numpy().reshape(-1), row=row.cpu().numpy().reshape(-1), max_rows=12)
@@ -113,7 +118,8 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
     _, _, _, ost = og.gfpush(ip, ix, sample.cpu().numpy(), coef, rmax, k)
     assert abs(st["edges_pushed"] - ost.edges_pushed) <= 1e-6 * ost.edges_pushed
     assert abs(st["frontier_total"] - ost.frontier_total) <= 1e-6 * ost.frontier_total
-    assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
+    if not graph.last_stats()["bucket_count"]:   # (default tuning: the bucket kernel's candidate merge does not count the support)
+        assert abs(st["support_total"] - ost.support_total) <= 1e-6 * ost.support_total
     del graph
     torch.cuda.empty_cache()
 
