@@ -595,14 +595,15 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             int e = b + 1;
             while (e < P.nb && tot + min(s_lcnt[e], (unsigned)P.capLog) <= (unsigned)kGroupPairs) { tot += min(s_lcnt[e], (unsigned)P.capLog); e++; }
             if (tot != 0 && !redo) {
+                // (read before the barrier below: the warps publish their next values right after their drain)
+                double tau_run = sm.wtau[0];
+#pragma unroll 8
+                for (int w = 1; w < BB / 32; w++) tau_run = fmin(tau_run, sm.wtau[w]);
                 // (the table held these nodes at every level, or they are fewer than kGroupPairs: it cannot overflow)
                 for (int bb = b; bb < e; bb++)
                     accumulate(log_id + (long long)bb * P.capLog, log_val + (long long)bb * P.capLog, min(s_lcnt[bb], (unsigned)P.capLog), kBuckets4);
                 __syncthreads();
                 // every claimed slot is one node of the support (its reserve may be exactly 0.0 in `single` mode)
-                double tau_run = sm.wtau[0];
-#pragma unroll 8
-                for (int w = 1; w < BB / 32; w++) tau_run = fmin(tau_run, sm.wtau[w]);
                 drain(tau_run);
                 if (rth <= 32) {   // the warp's rth-largest lane maximum (0.0 while fewer than rth lanes hold a positive reserve)
                     const long long r_val = warp_rth_largest(m1x, rth);
