@@ -54,6 +54,8 @@ int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree
 int g_push_bucket = 1;        // "push_bucket": the hash-bucket kernel (gfpush_bucket.cu) for supports far beyond shared memory:
                               // 0 off, 1 auto (where the slab kernel would run), 2 always
 int g_push_bucket_nb = 0;     // "push_bucket_nb": buckets per source (rounded up to a power of two); 0 = from the expected support
+int g_push_bucket_block = 0;  // "push_bucket_block": threads per CTA of the hash-bucket kernel: 1024 (one CTA per SM, 16 384-slot table), 512 (two per
+                              // SM, 8 192 slots each), 256 (three per SM, 4 096 slots); 0 = default
 int g_push_bucket_merge = 0;  // "push_bucket_merge": 0 = merge only the top-k candidates (the support is not counted), 1 = merge the whole reserve
 int g_push_max_clusters = 0;  // "push_max_clusters": cap on the resident clusters (0 = all the device schedules); scaling experiments
 int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments
@@ -1105,9 +1107,10 @@ int plan_cluster(gp_graph *g, long long S, int L, double rmax, int K, long long 
 }
 
 // ---- bucket kernel: planning -------------------------------------------------------------------------
-constexpr long long kPilotMinSources = 2048;   // calls with fewer sources are not worth the pilot's synchronisation
+constexpr long long kPilotMinSources = 2048;
+constexpr int kBucketDefaultBlock = 1024;   // (measured: profiles/r02_gfpush.md 5)   // calls with fewer sources are not worth the pilot's synchronisation
 struct BucketPlan {
-    int nb = 0, log_nb = 0;
+    int nb = 0, log_nb = 0, block = 0;
     long long ctas = 0, capPair = 0, capLog = 0, capP = 0, capS = 0;
     size_t bytes = 0;
     size_t off_pi = 0, off_pv = 0, off_li = 0, off_lv = 0, off_ps = 0, off_pl = 0, off_pa = 0, off_si = 0, off_sv = 0;
@@ -1115,11 +1118,13 @@ struct BucketPlan {
 
 // The bucket kernel replaces the slab kernel as the first pass where the slabs would run (supports far beyond the
 // shared-memory table) and the bucket counters fit shared memory; the slabs then only take what it hands over.
-void plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, long long support_hint, BucketPlan *bp) {
+int plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, long long support_hint, BucketPlan *bp) {
     *bp = BucketPlan{};
-    if (g_push_bucket == 0) return;
-    if (g_push_bucket == 1 && pl.hslots > 0) return;   // the shared-memory table tier takes this call
+    if (g_push_bucket == 0) return GP_OK;
+    if (g_push_bucket == 1 && pl.hslots > 0) return GP_OK;   // the shared-memory table tier takes this call
     const long long n = g->n;
+    const int block = g_push_bucket_block ? g_push_bucket_block : kBucketDefaultBlock;
+    const long long slots = gpb_slots(block);
     // a level pushes at most min(nnz + n, 1/rmax) edges
     long long capE = g->nnz + n;
     if (rmax > 0.0) capE = (long long)std::min<double>((double)capE, std::ceil(1.0 / rmax * 1.0001) + 16.0);
@@ -1132,13 +1137,16 @@ void plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, l
         while (nb < g_push_bucket_nb && nb < kBucketMaxBuckets) nb *= 2;
     } else {
         // (the probe sequence only runs out near a load of 1: the largest support seen may load the table to 0.9)
-        if (support_hint > 0) while (nb < kBucketMaxBuckets && support_hint > nb * (kBucketSlots * 9ll / 10)) nb *= 2;
-        else while (nb < kBucketMaxBuckets && std::min<long long>(n, capE + capE / 2) > nb * (kBucketSlots * 4ll / 5)) nb *= 2;
+        if (support_hint > 0) while (nb < kBucketMaxBuckets && support_hint > nb * (slots * 9ll / 10)) nb *= 2;
+        else while (nb < kBucketMaxBuckets && std::min<long long>(n, capE + capE / 2) > nb * (slots * 4ll / 5)) nb *= 2;
     }
     int log_nb = 0;
     while ((1ll << log_nb) < nb) log_nb++;
-    bp->nb = (int)nb; bp->log_nb = log_nb;
-    bp->ctas = g->num_sms;
+    bp->nb = (int)nb; bp->log_nb = log_nb; bp->block = block;
+    int per_sm = 1;
+    int rc = gpb_ctas_per_sm((int)nb, block, &per_sm);
+    if (rc != GP_OK) return rc;
+    bp->ctas = (long long)g->num_sms * per_sm;
     // a bucket stream holds four times its even share of a level (and at least 4096 pairs)
     bp->capPair = std::min<long long>(capE, std::max<long long>(4096, 4 * capE / nb));
     // the reserve log holds one entry per frontier node and level: at most 1 + (L-1) * capF in all
@@ -1146,6 +1154,8 @@ void plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, l
     bp->capP = pl.capF * 2 + 4096;   // push entries are cut into 128-edge chunks: at most capF nodes + capE / 128 chunks
     // the merged reserve: one slot per node of the support
     bp->capS = std::min<long long>(n, 1 + (long long)std::max(L - 1, 0) * pl.capF) + 16;
+    // (the kernel addresses a CTA's streams with 32-bit offsets)
+    if (nb * bp->capPair >= (1ll << 31) || nb * bp->capLog >= (1ll << 31)) { *bp = BucketPlan{}; return GP_OK; }
     const size_t c = (size_t)bp->ctas;
     size_t o = 0;
     bp->off_pi = o; o += align_up(c * nb * bp->capPair * 4, 256);
@@ -1158,6 +1168,7 @@ void plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, l
     bp->off_si = o; o += align_up(c * bp->capS * 4, 256);
     bp->off_sv = o; o += align_up(c * bp->capS * 8, 256);
     bp->bytes = o;
+    return GP_OK;
 }
 
 // CSR entries with the degree code in the spare high bits (built once per handle, on first use).
@@ -1200,7 +1211,10 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
         rc = plan_cluster(g, S, L, rmax, K, pl.capF, &cp);
         if (rc != GP_OK) return rc;
         const bool have_hint = g->support_hint > 0 && g->hint_L == L && g->hint_rmax == rmax;
-        if (cp.G == 0) plan_bucket(g, S, L, rmax, pl, have_hint ? g->support_hint : 0, &bp);
+        if (cp.G == 0) {
+            rc = plan_bucket(g, S, L, rmax, pl, have_hint ? g->support_hint : 0, &bp);
+            if (rc != GP_OK) return rc;
+        }
         // no measurement yet and enough sources to pay for one: the first sources run as a pilot (below)
         pilot = bp.nb > 0 && !have_hint && g_push_bucket_nb == 0 && S >= kPilotMinSources;
         if (cp.G > 0 || bp.nb > 0) {   // the slabs only back the first-pass kernel up
@@ -1296,7 +1310,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             }
             char *bb = (char *)g->bscratch;
             BucketPushParams B{};
-            B.node_rec = g->d_node_rec; B.packed = g->d_packed; B.n = (int)g->n; B.idbits = g->idbits; B.nb = b.nb; B.log_nb = b.log_nb;
+            B.node_rec = g->d_node_rec; B.packed = g->d_packed; B.n = (int)g->n; B.idbits = g->idbits; B.nb = b.nb; B.log_nb = b.log_nb; B.block = b.block;
             B.max_probe = std::max(g_push_cluster_probe, 1);
             B.full_merge = full_merge ? 1 : 0;
             B.node_idx = d_node_idx; B.S = last; B.it_base = first; B.coef = g->d_coef; B.L = L; B.rmax = rmax; B.K = K;
@@ -1324,7 +1338,8 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             GP_CUDA_TRY(cudaStreamSynchronize(stream));
             if (h_max > 0) {
                 g->support_hint = (long long)h_max; g->hint_L = L; g->hint_rmax = rmax;
-                plan_bucket(g, S, L, rmax, pl, g->support_hint, &bp);
+                rc = plan_bucket(g, S, L, rmax, pl, g->support_hint, &bp);
+                if (rc != GP_OK) return rc;
             }
             GP_CUDA_TRY(cudaMemsetAsync(g->d_ctrl, 0, sizeof(unsigned long long), stream));   // the queue restarts at `first`
         }
@@ -1344,7 +1359,7 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
     g->last.ctas = cp.G > 0 ? (long long)cp.clusters * cp.G : bp.nb > 0 ? std::min<long long>(bp.ctas, S) : std::min<long long>(pl.ctas, S);
     g->last.scratch_bytes = (int64_t)(g->scratch_bytes + g->cscratch_bytes + g->bscratch_bytes);
     g->last.scratch_mode = pl.mode; g->last.kernel_launches = launches; g->last.cluster_size = cp.G;
-    g->last.table_slots = cp.G > 0 ? kClusterSlots : bp.nb > 0 ? kBucketSlots : pl.hslots;
+    g->last.table_slots = cp.G > 0 ? kClusterSlots : bp.nb > 0 ? gpb_slots(bp.block) : pl.hslots;
     g->last.bucket_count = bp.nb;
     return GP_OK;
 }

@@ -28,23 +28,35 @@
 namespace gpp {
 namespace {
 
-constexpr int BB = kBucketBlock;
-constexpr int kSlots = kBucketSlots;    // slots of the shared-memory table
-constexpr int kBuckets4 = kSlots / 4;   // 4-key buckets of the table: one 16-byte shared-memory read per probe
-constexpr int SPT = kSlots / BB;        // table slots per thread in the scan
 constexpr int kEmpty = -1;
 constexpr int kChunk = 128;             // edges per push-list entry
 constexpr int kBigLen = 4096;           // longer entries stay whole and are expanded by all warps together
-constexpr int kBigCap = 32;
 constexpr int kItemBatch = 2;
-constexpr int kCandCap = 1024;
-constexpr int kCandMax = kSlots / 2;          // nodes the candidate merge can hold in one table fill
-constexpr int kGroupPairs = kSlots * 5 / 8;   // buckets are visited together while their pairs stay below this table load
+
+// Geometry of one CTA (template parameter BB = threads): the table has 16 slots per thread, so
+//   BB = 1024: one CTA per SM with a 16 384-slot table (192 KB);
+//   BB =  512: TWO CTAs per SM with 8 192-slot tables (96 KB each) -- two sources in flight per SM, the barriers and dependent
+//              shared-memory round trips of one overlap the other's (the kernel is latency-bound, profiles/r02_gfpush.md 5);
+//   BB =  256: three CTAs per SM with 4 096-slot tables.
+template <int BB>
+struct Geo {
+    static constexpr int kSlots = BB * 16;                // slots of the shared-memory table
+    static constexpr int kBuckets4 = kSlots / 4;          // 4-key buckets of the table: one 16-byte shared-memory read per probe
+    static constexpr int SPT = kSlots / BB;               // table slots per thread in the scan
+    static constexpr int kHashBits = BB == 1024 ? 12 : BB == 512 ? 11 : 10;   // log2(kBuckets4)
+    static constexpr int kBigCap = BB == 1024 ? 32 : 8;
+    static constexpr int kListCap = BB == 1024 ? 1024 : BB * 3 / 4;   // push-list entries / top-k survivors kept in shared memory
+    static constexpr int kCandCap = BB;                   // push candidates of one table scan kept in shared memory
+    static constexpr int kCandMax = kSlots / 2;           // nodes the candidate merge can hold in one table fill
+    static constexpr int kGroupPairs = kSlots * 5 / 8;    // buckets are visited together while their pairs stay below this table load
+    static constexpr int kMinCtas = BB == 1024 ? 1 : BB == 512 ? 2 : 3;
+};
 
 __device__ __forceinline__ unsigned hash_node(unsigned id) { return id * 2654435761u; }
 
 // Slot of packed node `vp` in the table (claiming one when it is new), or -1 when `max_probe` buckets hold neither it nor an
 // empty slot.  Keys are never removed while a bucket is live and empties are taken in index order, so an observed key is final.
+template <int kBuckets4>
 __device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int max_probe, bool &claimed) {
     unsigned b = bucket;
     claimed = false;
@@ -80,6 +92,7 @@ __device__ __forceinline__ long long warp_rth_largest(long long v, int r) {
 }
 
 // Slot of packed node `vp` if the table holds it, else -1 (never claims).
+template <int kBuckets4>
 __device__ __forceinline__ int lookup_slot(const int *keys, unsigned bucket, int vp) {
     unsigned b = bucket;
     for (int probe = 0; probe < kBuckets4; probe++, b = (b + 1) & (kBuckets4 - 1)) {
@@ -93,40 +106,48 @@ __device__ __forceinline__ int lookup_slot(const int *keys, unsigned bucket, int
     return -1;
 }
 
+template <int BB>
 struct BSmem {
-    int start[BB];             // push list of the level: first BB entries {start, len, add}; during the top-k (the list is
-                               // dead then) `add` / `start` hold the survivors of the pre-filter
-    unsigned len[BB];
-    double add[BB];
+    int start[Geo<BB>::kListCap];   // push list of the level: first kListCap entries {start, len, add}; during the top-k (the
+                                    // list is dead then) `add` / `start` hold the survivors of the pre-filter
+    unsigned len[Geo<BB>::kListCap];
+    double add[Geo<BB>::kListCap];
     unsigned warp_scan[BB / 32 + 1];
     double wtau[BB / 32];
     union {
-        struct {
-            unsigned hist[kHistBins];
-            unsigned long long bkey[kBucketCap];
-            int bid[kBucketCap];
+        struct {   // top-k (block_topk): the histogram is dead once the boundary bucket is collected
+            union {
+                unsigned hist[kHistBins];
+                struct {
+                    unsigned long long bkey[kBucketCap];
+                    int bid[kBucketCap];
+                };
+            };
         } sel;
         struct {
-            double r[kCandCap];
-            unsigned key[kCandCap];
+            double r[Geo<BB>::kCandCap];
+            unsigned key[Geo<BB>::kCandCap];
         } cand;
     };
     long long it;
     int n_push, n_sel, n_sup, n_all, n_list, next_item, n_big, n_cand;   // n_sup: reserves written out, n_all: nodes of the support
-    int big_st[kBigCap];
-    unsigned big_len[kBigCap];
-    double big_add[kBigCap];
+    int big_st[Geo<BB>::kBigCap];
+    unsigned big_len[Geo<BB>::kBigCap];
+    double big_add[Geo<BB>::kBigCap];
     int n_out, n_bucket;
     int sel_bin, sel_above, sel_inbin;
     int ovf;
     int full;                  // a probe sequence ran out: the source goes to the slab kernel, stop probing
-    long long tau_bits;
     double tau_lb;             // a lower bound of the source's K-th largest reserve, from the levels settled so far
     long long ph[8], t_prev;
 };
 
-__global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushParams P) {
-    __shared__ BSmem sm;
+template <int BB>
+__global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(const BucketPushParams P) {
+    constexpr int kSlots = Geo<BB>::kSlots, kBuckets4 = Geo<BB>::kBuckets4, SPT = Geo<BB>::SPT, kHashBits = Geo<BB>::kHashBits;
+    constexpr int kBigCap = Geo<BB>::kBigCap, kListCap = Geo<BB>::kListCap, kCandCap = Geo<BB>::kCandCap;
+    constexpr int kCandMax = Geo<BB>::kCandMax, kGroupPairs = Geo<BB>::kGroupPairs;
+    __shared__ BSmem<BB> sm;
     extern __shared__ __align__(16) double s_vals[];                                  // [kSlots] the bucket's residues / reserves
     int *s_keys = reinterpret_cast<int *>(s_vals + kSlots);             // [kSlots] packed node, kEmpty = free
     unsigned *s_cnt = reinterpret_cast<unsigned *>(s_keys + kSlots);    // [nb] pairs per bucket (this level)
@@ -149,6 +170,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
     int *sup_id = P.sup_id + cta * P.capS;
     double *sup_val = P.sup_val + cta * P.capS;
     unsigned long long *err = P.stats + 3;
+    const unsigned capPair32 = (unsigned)P.capPair, capLog32 = (unsigned)P.capLog;   // (nb * cap < 2^31: plan_bucket)
     const int capC = (int)min((long long)kCandMax, P.capS);   // the candidate list lives in sup_id until the merge
 
     for (int i = tid; i < kSlots; i += BB) { s_vals[i] = 0.0; s_keys[i] = kEmpty; }
@@ -196,7 +218,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             for (unsigned o = 0; o < e_len; o += step) {
                 const int p = atomicAdd(&sm.n_push, 1);
                 const unsigned l = min(step, e_len - o);
-                if (p < BB) { sm.start[p] = e_start + (int)o; sm.len[p] = l; sm.add[p] = e_add; }
+                if (p < kListCap) { sm.start[p] = e_start + (int)o; sm.len[p] = l; sm.add[p] = e_add; }
                 else if (p < P.capP) { push_start[p] = e_start + (int)o; push_len[p] = (int)l; push_add[p] = e_add; }
                 else ovf = true;
             }
@@ -227,7 +249,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                 int st[4];     // 0 skip, 1 key found, 2 free slot to claim, 3 bucket holds other keys only
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - 12)) & (kBuckets4 - 1);
+                    const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1);
                     const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * hb);
                     const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
                     at[q] = 4 * (int)hb; st[q] = 3;
@@ -249,7 +271,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                     if (st[q] == 2 && won[q] != kEmpty && won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
                     if (st[q] == 3) {
                         bool claimed;
-                        at[q] = find_slot(s_keys, (unsigned)at[q] >> 2, vp[q], max_probe, claimed);
+                        at[q] = find_slot<kBuckets4>(s_keys, (unsigned)at[q] >> 2, vp[q], max_probe, claimed);
                         if (at[q] < 0) { ovf = true; sm.full = 1; st[q] = 0; }
                     }
                 }
@@ -293,7 +315,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             };
             auto store = [&](const int vp, const double av, const bool ok, const unsigned b, const unsigned pos) {
                 if (ok) {
-                    if (pos < (unsigned)P.capPair) { pair_id[(long long)b * P.capPair + pos] = vp; pair_val[(long long)b * P.capPair + pos] = av; }
+                    if (pos < (unsigned)P.capPair) { const unsigned o = b * capPair32 + pos; pair_id[o] = vp; pair_val[o] = av; }
                     else ovf = true;
                 }
             };
@@ -305,7 +327,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             auto load_item = [&](const int i, int &st, unsigned &len, double &add) {
                 st = 0; len = 0; add = 0.0;
                 if (i < n_items) {
-                    if (i < BB) { st = sm.start[i]; len = sm.len[i]; add = sm.add[i]; }
+                    if (i < kListCap) { st = sm.start[i]; len = sm.len[i]; add = sm.add[i]; }
                     else { st = push_start[i]; len = (unsigned)push_len[i]; add = push_add[i]; }
                 }
             };
@@ -451,7 +473,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                             if (got[q]) {
                                 src_front++;
                                 const double cr = c * rr[q];
-                                if (pos[q] < (unsigned)P.capLog) { log_id[(long long)lb[q] * P.capLog + pos[q]] = (int)key[q]; log_val[(long long)lb[q] * P.capLog + pos[q]] = cr; }
+                                if (pos[q] < (unsigned)P.capLog) { const unsigned o = lb[q] * capLog32 + pos[q]; log_id[o] = (int)key[q]; log_val[o] = cr; }
                                 else ovf = true;
                                 lvl_max = max(lvl_max, __double_as_longlong(cr));
                                 if (!defer && cr >= cand_thr) {   // (rare once the first two or three levels have set tau_lb)
@@ -485,10 +507,8 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             if (!P.full_merge && P.K <= BB) {
                 // tau_lb: the K-th largest of the threads' largest contributions of this level -- K different nodes whose
                 // reserve is at least that (a level's nodes are distinct, contributions only add up)
-                if (tid == 0) sm.tau_bits = 0x7fffffffffffffffll;
-                auto each_max = [&](auto f) { if (lvl_max > 0) f(__longlong_as_double(lvl_max), 0); };
-                const int n_max = block_topk<BB>(sm, P.K, false, each_max, [&](int, int, double v) { atomicMin(&sm.tau_bits, __double_as_longlong(v)); });
-                if (tid == 0 && n_max >= P.K) sm.tau_lb = fmax(sm.tau_lb, __longlong_as_double(sm.tau_bits));
+                const double lvl_bound = block_kth_lower_bound<BB>(sm, P.K, lvl_max);   // (one histogram pass: within 1/32 of the K-th largest)
+                if (tid == 0 && lvl_bound > sm.tau_lb) sm.tau_lb = lvl_bound;
                 __syncthreads();
                 if (defer) {   // this level's log entries (just written: L2) against the bound the level itself gave
                     const double thr = sm.tau_lb / (double)P.L * (1.0 - 1e-9);
@@ -510,10 +530,10 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
         const bool redo = sm.ovf != 0;
         // ------------------------------------------------------------------ reserve: merge the logs bucket by bucket
         // Only reserves that can still be among the K largest are written out: a running threshold tau_run with at least K
-        // reserves >= it.  Every warp publishes the r-th largest of its lanes' maxima, r = ceil(K / 32) (a lane's maximum is a
+        // reserves >= it.  Every warp publishes the r-th largest of its lanes' maxima, r = ceil(K / warps) (a lane's maximum is a
         // node of its own, so the warp has seen r reserves >= that value); the minimum over the warps bounds K of them.  The
         // published values only grow, so a reader that sees a mix of old and new ones still holds a valid (lower) bound.
-        const int rth = (P.K + 31) / 32;
+        const int rth = (P.K + BB / 32 - 1) / (BB / 32);
         if (tid == 0) {
             sm.n_sup = 0; sm.n_all = 0;
         }
@@ -563,7 +583,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             for (int i = tid; i < n_cand; i += BB) {
                 const int vp = sup_id[i];
                 bool claimed;
-                find_slot(s_keys, (hash_node((unsigned)vp & idmask) >> (bshift - 12)) & (kBuckets4 - 1), vp, kBuckets4, claimed);
+                find_slot<kBuckets4>(s_keys, (hash_node((unsigned)vp & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1), vp, kBuckets4, claimed);
             }
             __syncthreads();
             for (int b = 0; b < P.nb; b++) {
@@ -577,7 +597,7 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         at[q] = -1;
-                        if (vp[q] != kEmpty) at[q] = lookup_slot(s_keys, (hash_node((unsigned)vp[q] & idmask) >> (bshift - 12)) & (kBuckets4 - 1), vp[q]);
+                        if (vp[q] != kEmpty) at[q] = lookup_slot<kBuckets4>(s_keys, (hash_node((unsigned)vp[q] & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1), vp[q]);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; q++)
@@ -627,12 +647,9 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
             st_frontier += src_front; st_edges += src_edges;
             st_support += src_support;
             // Threshold: the K-th largest of the threads' maxima -- every thread's maximum is a distinct node's reserve, so at
-            // least K reserves are >= tau and nothing below tau can be among the K largest (K <= threads).  Found with the
-            // same radix select (one item per thread); the minimum of its winners is tau.
-            if (tid == 0) sm.tau_bits = 0x7fffffffffffffffll;
-            auto each_max = [&](auto f) { if (m1x > 0) f(__longlong_as_double(m1x), 0); };
-            const int n_max = block_topk<BB>(sm, P.K, false, each_max, [&](int, int, double v) { atomicMin(&sm.tau_bits, __double_as_longlong(v)); });
-            const double tau = n_max >= P.K ? __longlong_as_double(sm.tau_bits) : 0.0;
+            // least K reserves are >= tau and nothing below tau can be among the K largest (K <= threads); any lower bound of
+            // it serves as well.
+            const double tau = block_kth_lower_bound<BB>(sm, P.K, m1x);   // (a lower bound within 1/32 of it: a few more survivors)
             if (tid == 0) sm.n_list = 0;
             __syncthreads();
             bool listed = tau > 0.0;
@@ -645,12 +662,12 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
                     for (int q = 0; q < 4; q++) {
                         if (x[q] >= tau) {
                             const int pos = atomicAdd(&sm.n_list, 1);
-                            if (pos < BB) { sm.add[pos] = x[q]; sm.start[pos] = sup_id[j0 + q * BB]; }
+                            if (pos < kListCap) { sm.add[pos] = x[q]; sm.start[pos] = sup_id[j0 + q * BB]; }
                         }
                     }
                 }
                 __syncthreads();
-                listed = sm.n_list <= BB;
+                listed = sm.n_list <= kListCap;
             }
             const int n_list = listed ? sm.n_list : 0;
             auto each = [&](auto f) {
@@ -699,18 +716,46 @@ __global__ void __launch_bounds__(BB, 1) gfpush_bucket_kernel(const BucketPushPa
 
 }  // namespace
 
-size_t gpb_dynamic_smem(int nb) { return (size_t)kSlots * 12 + (size_t)nb * 12; }
+size_t gpb_dynamic_smem(int nb, int block) { return (size_t)gpb_slots(block) * 12 + (size_t)nb * 12; }
 
-int gpb_launch(const BucketPushParams &P, int ctas, cudaStream_t stream) {
+namespace {
+template <int BB>
+int configure_kernel(size_t smem) {
     static size_t configured = 0;
-    const size_t smem = gpb_dynamic_smem(P.nb);
     if (smem > configured) {
-        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_bucket_kernel<BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GP_CUDA_TRY(cudaFuncSetAttribute(gfpush_bucket_kernel<BB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = smem;
     }
-    gfpush_bucket_kernel<<<(unsigned)ctas, BB, smem, stream>>>(P);
+    return GP_OK;
+}
+template <int BB>
+int resident_ctas(int nb, int *per_sm) {
+    const size_t smem = gpb_dynamic_smem(nb, BB);
+    int rc = configure_kernel<BB>(smem);
+    if (rc != GP_OK) return rc;
+    int n = 0;
+    GP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gfpush_bucket_kernel<BB>, BB, smem));
+    *per_sm = n < 1 ? 1 : n;
+    return GP_OK;
+}
+template <int BB>
+int launch(const BucketPushParams &P, int ctas, cudaStream_t stream) {
+    const size_t smem = gpb_dynamic_smem(P.nb, BB);
+    int rc = configure_kernel<BB>(smem);
+    if (rc != GP_OK) return rc;
+    gfpush_bucket_kernel<BB><<<(unsigned)ctas, BB, smem, stream>>>(P);
     GP_CUDA_TRY(cudaGetLastError());
     return GP_OK;
+}
+}  // namespace
+
+int gpb_ctas_per_sm(int nb, int block, int *per_sm) {
+    return block == 256 ? resident_ctas<256>(nb, per_sm) : block == 512 ? resident_ctas<512>(nb, per_sm) : resident_ctas<1024>(nb, per_sm);
+}
+
+int gpb_launch(const BucketPushParams &P, int ctas, cudaStream_t stream) {
+    return P.block == 256 ? launch<256>(P, ctas, stream) : P.block == 512 ? launch<512>(P, ctas, stream) : launch<1024>(P, ctas, stream);
 }
 
 }  // namespace gpp

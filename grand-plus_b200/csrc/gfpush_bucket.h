@@ -4,8 +4,9 @@
 
 namespace gpp {
 
-constexpr int kBucketBlock = 1024;       // threads per CTA
-constexpr int kBucketSlots = 16384;      // slots of the shared-memory {key, residue} table
+// threads per CTA: 1024 (one CTA per SM), 512 (two per SM) or 256 (three per SM); the shared-memory {key, residue} table has
+// 16 slots per thread
+constexpr int gpb_slots(int block) { return block * 16; }
 constexpr int kBucketMaxBuckets = 256;   // bucket counters live in shared memory
 
 struct BucketPushParams {
@@ -13,6 +14,7 @@ struct BucketPushParams {
     const int *packed;         // [nnz] neighbour id | degree code << idbits (gpc_pack_indices)
     int n;
     int idbits;
+    int block;                 // threads per CTA: 1024, 512 or 256 (gpb_slots(block) table slots)
     int nb;                    // buckets = 2^log_nb (>= 2): bucket of a node = hash(node) >> (32 - log_nb)
     int log_nb;
     int max_probe;             // 4-key buckets of the table tried before the source is handed to the slab kernel
@@ -35,7 +37,7 @@ struct BucketPushParams {
     int *log_id;               // [ctas][nb][capLog]   reserve log of the source, by bucket: packed node
     double *log_val;           // [ctas][nb][capLog]   ... and coef * r
     long long capLog;
-    int *push_start;           // [ctas][capP]  push list of the level beyond the first 1024 entries
+    int *push_start;           // [ctas][capP]  push list of the level beyond the entries kept in shared memory
     int *push_len;
     double *push_add;
     long long capP;
@@ -51,7 +53,8 @@ struct BucketPushParams {
     unsigned long long *redo_count;
 };
 
-size_t gpb_dynamic_smem(int nb);
+size_t gpb_dynamic_smem(int nb, int block);
+int gpb_ctas_per_sm(int nb, int block, int *per_sm);   // resident CTAs per SM of that geometry (occupancy query)
 int gpb_launch(const BucketPushParams &P, int ctas, cudaStream_t stream);
 
 }  // namespace gpp

@@ -138,5 +138,29 @@ __device__ __forceinline__ int block_topk(Smem &sm, const int K, const bool smal
     return sm.n_out;
 }
 
+// A LOWER BOUND of the K-th largest of the threads' values (one per thread, `vbits` = bit pattern of a non-negative double
+// <= 1, 0 = none), within 1/32 of it: ONE histogram pass over 6 exponent bits + 5 mantissa bits (2^-63 .. 1; smaller
+// values share bin 0, which gives no bound) instead of the full radix select -- for thresholds, where any lower bound is
+// correct and a tight one only saves work.  Returns 0.0 when fewer than K values are positive.  Every thread of the CTA
+// must call it; uses sm.sel.hist, sm.warp_scan, sm.sel_bin / sel_above / sel_inbin.
+template <int CB, class Smem>
+__device__ __forceinline__ double block_kth_lower_bound(Smem &sm, const int K, const long long vbits) {
+    constexpr long long kBinBase = (1023ll - 63ll) << 5;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kHistBins; i += CB) sm.sel.hist[i] = 0;
+    __syncthreads();
+    if (vbits > 0) {
+        long long t = (vbits >> 47) - kBinBase;
+        t = t < 0 ? 0 : (t > kHistBins - 1 ? kHistBins - 1 : t);
+        atomicAdd(&sm.sel.hist[(int)t], 1u);
+    }
+    __syncthreads();
+    const unsigned total = select_bin_generic<CB>(sm.sel.hist, sm.warp_scan, kHistBins, K, false, &sm.sel_bin, &sm.sel_above, &sm.sel_inbin);
+    if (total < (unsigned)K) return 0.0;
+    const int bin = sm.sel_bin;
+    if (bin <= 0) return 0.0;
+    return __longlong_as_double(((long long)bin + kBinBase) << 47);   // the lower edge of the K-th largest value's bin
+}
+
 
 }  // namespace gpp

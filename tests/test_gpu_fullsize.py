@@ -23,8 +23,10 @@ SHAPES = {
 TIER_TUNING = {"cluster": dict(push_cluster=1, push_bucket=0), "table": dict(push_cluster=0, push_smem_hash=2, push_bucket=0),
                "bucket": dict(push_cluster=0, push_smem_hash=0, push_bucket=2, push_bucket_merge=1),
                "bucket_cand": dict(push_cluster=0, push_smem_hash=0, push_bucket=2, push_bucket_merge=0),
+               "bucket_cand_b512": dict(push_cluster=0, push_smem_hash=0, push_bucket=2, push_bucket_merge=0, push_bucket_block=512),
+               "bucket_cand_b256": dict(push_cluster=0, push_smem_hash=0, push_bucket=2, push_bucket_merge=0, push_bucket_block=256),
                "slabs": dict(push_cluster=0, push_smem_hash=0, push_bucket=0)}
-TUNING_DEFAULTS = dict(push_cluster=0, push_smem_hash=1, push_bucket=1, push_bucket_merge=0)
+TUNING_DEFAULTS = dict(push_cluster=0, push_smem_hash=1, push_bucket=1, push_bucket_merge=0, push_bucket_block=0)
 
 
 def _build(shape):
@@ -58,12 +60,13 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
     indptr, indices, graph, src = request.getfixturevalue("reddit_shape") if shape == "reddit" else _build(shape)
     coef = og.coef_for("ppr", order, alpha)
     # (the MAG-shape graph has 644 buckets with ~30 pushed edges each: the bucket kernel is correct there but is not its home)
-    tiers = {"reddit": ("cluster", "table", "bucket", "bucket_cand", "slabs"), "amazon2m": ("cluster", "bucket", "bucket_cand", "slabs"),
+    tiers = {"reddit": ("cluster", "table", "bucket", "bucket_cand", "bucket_cand_b512", "bucket_cand_b256", "slabs"),
+             "amazon2m": ("cluster", "bucket", "bucket_cand", "bucket_cand_b512", "bucket_cand_b256", "slabs"),
              "mag": ("cluster", "table", "slabs")}[shape]
     out = {}
     try:
         for tier in tiers:
-            for key, v in TIER_TUNING[tier].items():
+            for key, v in {**TUNING_DEFAULTS, **TIER_TUNING[tier]}.items():
                 _lib.set_tuning(key, v)
             graph.cumulative_stats(reset=True)
             row, col, val, _ = graph.gfpush_device(src, coef, rmax, k, want_fp32=True, check=True)
@@ -83,7 +86,7 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
         _, ca, va, sa, _ = out[tier]
         # work counters are integers of the algorithm: every kernel counts the same pushes, frontiers and supports
         for key in ("edges_pushed", "frontier_total", "support_total", "sources"):
-            if tier == "bucket_cand" and key == "support_total":
+            if tier.startswith("bucket_cand") and key == "support_total":
                 assert sa[key] <= 0.1 * sb[key]   # the candidate merge never materialises the support (hand-overs and fall-backs do)
                 continue
             assert abs(sa[key] - sb[key]) <= 1e-6 * sb[key], (tier, key, sa[key], sb[key])
@@ -101,7 +104,7 @@ def test_gfpush_full_size_tiers_agree_and_match_oracle(shape, request):
         assert float(sums.max()) <= 1.0 + 1e-12 and float(sums.min()) >= coef[0] * (1 - 1e-12)
     # the oracle itself on a sample of rows (hub source included), rows and work counters
     ip, ix = indptr.cpu().numpy(), indices.cpu().numpy()
-    for bt in ("bucket", "bucket_cand"):
+    for bt in ("bucket", "bucket_cand", "bucket_cand_b512", "bucket_cand_b256"):
         if bt in out:
             sbk = out[bt][3]
             assert sbk["cluster_sources"] + sbk["redo_sources"] == len(src) and sbk["redo_sources"] <= 0.02 * len(src), sbk

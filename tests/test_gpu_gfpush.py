@@ -204,7 +204,7 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
-    DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+    DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_bucket_block": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
                 "push_smem_probe": 2, "push_max_ctas": 0}
 
     def __init__(self, **kv):
@@ -232,6 +232,12 @@ TIERS = {
     "bucket_cand": dict(push_cluster=0, push_smem_hash=0, push_bucket=1, push_bucket_merge=0),   # merges only the top-k candidates
     "bucket_cand_forced": dict(push_cluster=0, push_bucket=2, push_bucket_merge=0),
     "bucket_cand_nb8": dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_nb=8),
+    # two / three sources per SM: 512-thread CTAs with 8 192-slot tables, 256-thread CTAs with 4 096-slot tables
+    "bucket_b512": dict(push_cluster=0, push_bucket=2, push_bucket_merge=1, push_bucket_block=512),
+    "bucket_cand_b512": dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_block=512),
+    "bucket_b256": dict(push_cluster=0, push_bucket=2, push_bucket_merge=1, push_bucket_block=256),
+    "bucket_cand_b256": dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_block=256),
+    "bucket_cand_b1024": dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_block=1024),
     "smem": dict(push_cluster=0, push_smem_hash=2),
     "smem_probe1": dict(push_cluster=0, push_smem_hash=2, push_smem_probe=1),
     "smem_probe2": dict(push_cluster=0, push_smem_hash=2, push_smem_probe=2),

@@ -15,10 +15,11 @@ for kv in (dict(push_cluster=0, push_smem_hash=2, push_smem_probe=4), dict(push_
            dict(push_cluster=0, push_smem_hash=0, push_bucket=0), dict(scratch=1),
            dict(push_cluster=-1), dict(push_cluster=2), dict(push_cluster=4, push_hub_deg=8), dict(push_cluster=16),
            dict(push_cluster=2, push_cluster_probe=1), dict(push_cluster=0, push_bucket=2, push_bucket_merge=1),
-           dict(push_cluster=0, push_bucket=2, push_bucket_merge=0), dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_nb=8)):
+           dict(push_cluster=0, push_bucket=2, push_bucket_merge=0), dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_nb=8),
+           dict(push_cluster=0, push_bucket=2, push_bucket_merge=0, push_bucket_block=512), dict(push_cluster=0, push_bucket=2, push_bucket_merge=1, push_bucket_block=256)):
     if os.environ.get("SANITIZE_ONLY") and not any(os.environ["SANITIZE_ONLY"] in k for k in kv): continue   # e.g. SANITIZE_ONLY=bucket
     scratch = kv.pop("scratch", 2)
-    for k, v in {**dict(push_bucket=1, push_bucket_merge=0, push_bucket_nb=0, push_cluster_probe=128, push_hub_deg=0), **kv}.items(): _lib.set_tuning(k, v)
+    for k, v in {**dict(push_bucket=1, push_bucket_merge=0, push_bucket_nb=0, push_bucket_block=0, push_cluster_probe=128, push_hub_deg=0), **kv}.items(): _lib.set_tuning(k, v)
     g = propagation.Graph(indptr, indices, 0); g.configure(scratch_mode=scratch)
     S, K = len(src), 16
     row = np.zeros(S*K, np.int32); col = np.zeros(S*K, np.int32); val = np.zeros(S*K, np.float64)

@@ -16,7 +16,7 @@ import bench  # noqa: E402
 from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
-DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_bucket_block": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
             "push_smem_probe": 2, "push_max_ctas": 0}
 
 
@@ -41,8 +41,9 @@ def main():
     coef = bench.coef_for(w["mode"], w["order"], w["alpha"])
     batches = bench.source_batches(n, S, steps + 2, 0, 1, dev)
     graph = propagation.Graph.from_device_csr(indptr, indices)
-    if os.environ.get("SWEEP_SCRATCH"):
-        graph.configure(scratch_mode=int(os.environ["SWEEP_SCRATCH"]))
+    if os.environ.get("SWEEP_SCRATCH") or os.environ.get("SWEEP_BLOCK") or os.environ.get("SWEEP_PER_SM"):
+        graph.configure(scratch_mode=int(os.environ.get("SWEEP_SCRATCH", "0")), block_threads=int(os.environ.get("SWEEP_BLOCK", "0")),
+                        ctas_per_sm=int(os.environ.get("SWEEP_PER_SM", "0")))
     for cfg in configs:
         kv = dict(DEFAULTS)
         for item in cfg.split(","):
