@@ -130,6 +130,7 @@ struct BSmem {
         } cand;
     };
     long long it;
+    unsigned n_edges;          // pushed edges of the level being built (sum of the push-list entries' lengths)
     int n_push, n_sel, n_sup, n_all, n_list, next_item, n_big, n_cand;   // n_sup: reserves written out, n_all: nodes of the support
     int big_st[Geo<BB>::kBigCap];
     unsigned big_len[Geo<BB>::kBigCap];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
     for (int i = tid; i < kSlots; i += BB) { s_vals[i] = 0.0; s_keys[i] = kEmpty; }
     for (int i = tid; i < P.nb; i += BB) { s_cnt[i] = 0; s_lcnt[i] = 0; }
     if (tid == 0) {
-        sm.n_push = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; sm.ovf = 0; sm.full = 0;
+        sm.n_push = 0; sm.n_edges = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; sm.ovf = 0; sm.full = 0;
         for (int i = 0; i < 8; i++) sm.ph[i] = 0;
     }
     unsigned long long st_sources = 0, st_redo = 0;      // thread 0
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
 
         // A push-list entry {start, len, add = r / deg}, cut into chunks of kChunk edges (the unit one warp expands).
         auto add_entry = [&](int e_start, unsigned e_len, double e_add) {
+            atomicAdd(&sm.n_edges, e_len);
             const unsigned step = e_len > (unsigned)kBigLen ? e_len : (unsigned)kChunk;
             for (unsigned o = 0; o < e_len; o += step) {
                 const int p = atomicAdd(&sm.n_push, 1);
@@ -234,6 +236,43 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
         // of dependent shared-memory operations (32 warps per SM, each find-or-claim + add is a chain of four), so a thread
         // takes its pairs four at a time and runs every step for all four before the next one: four key-bucket reads, four
         // claims, four adds are in flight together.  The home bucket settles ~9 of 10 pairs; the rest take find_slot.
+        auto accum4 = [&](const int (&vp)[4], const double (&av)[4], const int max_probe) {   // (vp == kEmpty: no pair)
+            int at[4];     // slot of the key / of the first free slot in the home bucket
+            int st[4];     // 0 skip, 1 key found, 2 free slot to claim, 3 bucket holds other keys only
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1);
+                const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * hb);
+                const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+                at[q] = 4 * (int)hb; st[q] = 3;
+#pragma unroll
+                for (int i = 3; i >= 0; i--) {   // (free slots are taken in index order: the first free one ends the search)
+                    if (kk[i] == vp[q]) { st[q] = 1; at[q] = 4 * (int)hb + i; }
+                    else if (kk[i] == kEmpty) { st[q] = 2; at[q] = 4 * (int)hb + i; }
+                }
+                if (vp[q] == kEmpty) st[q] = 0;
+            }
+            int won[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                won[q] = 0;
+                if (st[q] == 2) won[q] = atomicCAS(s_keys + at[q], kEmpty, vp[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (st[q] == 2 && won[q] != kEmpty && won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
+                if (st[q] == 3) {
+                    bool claimed;
+                    at[q] = find_slot<kBuckets4>(s_keys, (unsigned)at[q] >> 2, vp[q], max_probe, claimed);
+                    if (at[q] < 0) { ovf = true; sm.full = 1; st[q] = 0; }
+                }
+            }
+            // (atomicAdd on a shared-memory double is ptxas' ATOMS.CAST.SPIN loop; a hand-written compare-and-swap against
+            // 0.0 for freshly claimed slots measured SLOWER than leaving every add to it)
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                if (st[q] != 0) atomicAdd(s_vals + at[q], av[q]);
+        };
         auto accumulate = [&](const int *ids, const double *vals, const unsigned n, const int max_probe) {
             for (unsigned i0 = tid; i0 < n; i0 += BB * 4) {
                 int vp[4];
@@ -241,45 +280,11 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const unsigned i = i0 + BB * q;
-                    vp[q] = kEmpty; av[q] = 0.0;   // (kEmpty is not a node: the pair is skipped below)
+                    vp[q] = kEmpty; av[q] = 0.0;   // (kEmpty is not a node: the pair is skipped)
                     if (i < n) { vp[q] = __ldcs(ids + i); av[q] = __ldcs(vals + i); }
                 }
                 if (*(volatile int *)&sm.full) break;
-                int at[4];     // slot of the key / of the first free slot in the home bucket
-                int st[4];     // 0 skip, 1 key found, 2 free slot to claim, 3 bucket holds other keys only
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1);
-                    const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * hb);
-                    const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
-                    at[q] = 4 * (int)hb; st[q] = 3;
-#pragma unroll
-                    for (int i = 3; i >= 0; i--) {   // (free slots are taken in index order: the first free one ends the search)
-                        if (kk[i] == vp[q]) { st[q] = 1; at[q] = 4 * (int)hb + i; }
-                        else if (kk[i] == kEmpty) { st[q] = 2; at[q] = 4 * (int)hb + i; }
-                    }
-                    if (vp[q] == kEmpty) st[q] = 0;
-                }
-                int won[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    won[q] = 0;
-                    if (st[q] == 2) won[q] = atomicCAS(s_keys + at[q], kEmpty, vp[q]);
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (st[q] == 2 && won[q] != kEmpty && won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
-                    if (st[q] == 3) {
-                        bool claimed;
-                        at[q] = find_slot<kBuckets4>(s_keys, (unsigned)at[q] >> 2, vp[q], max_probe, claimed);
-                        if (at[q] < 0) { ovf = true; sm.full = 1; st[q] = 0; }
-                    }
-                }
-                // (atomicAdd on a shared-memory double is ptxas' ATOMS.CAST.SPIN loop; a hand-written compare-and-swap against
-                // 0.0 for freshly claimed slots measured SLOWER than leaving every add to it)
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (st[q] != 0) atomicAdd(s_vals + at[q], av[q]);
+                accum4(vp, av, max_probe);
             }
         };
         // ------------------------------------------------------------------ level 0 (graph.h:80-82)
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
         const bool push0 = P.L > 1 && (deg0 == 0 || 1.0 >= P.rmax * (double)deg0);
         if (tid == 0) {
             st_sources++;
-            sm.n_push = 0;
+            sm.n_push = 0; sm.n_edges = 0;
             if (push0) {
                 if (deg0 == 0) add_entry(-1, 1u, 1.0);
                 else add_entry(src_rec.x, deg0, 1.0 / (double)deg0);
@@ -306,6 +311,10 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
         for (int level = 0; level < P.L - 1; level++) {   // graph.h:83
             const int n_items = min((long long)sm.n_push, P.capP);
             if (n_items == 0) break;   // nothing pushes: every later residue is zero (the reserve is complete)
+            // A level whose pushed edges all fit ONE table fill (the usual case when a source's support is of the order of the
+            // table: Reddit-, MAG-shape) skips the bucket streams: the edges are accumulated straight into the table.
+            const unsigned level_edges = sm.n_edges;
+            const bool direct = level_edges <= (unsigned)kGroupPairs;
             // ---------------------------------------------------------------- expand (graph.h:94-100): append to the buckets
             // Reserve a position in the node's bucket stream / store the pair there: split so that a batch of edges issues all
             // its counter updates before the first dependent store.
@@ -320,6 +329,12 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 }
             };
             auto sink = [&](const int vp, const double av, const bool ok) {
+                if (direct) {
+                    const int v4[4] = {ok ? vp : kEmpty, kEmpty, kEmpty, kEmpty};
+                    const double a4[4] = {av, 0.0, 0.0, 0.0};
+                    accum4(v4, a4, P.max_probe);
+                    return;
+                }
                 unsigned b;
                 const unsigned pos = reserve(vp, ok, b);
                 store(vp, av, ok, b, pos);
@@ -369,6 +384,17 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                         if (st[k] >= 0 && (unsigned)(32 * q + lane) < len[k]) vp[k][q] = __ldcs(P.packed + st[k] + 32 * q + lane);   // graph.h:96-97
                     }
                 }
+                if (direct) {
+#pragma unroll
+                    for (int k = 0; k < kItemBatch; k++) {
+                        int v4[4];
+                        double a4[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { v4[q] = (unsigned)(32 * q + lane) < len[k] ? vp[k][q] : kEmpty; a4[q] = add[k]; }
+                        if (len[k]) accum4(v4, a4, P.max_probe);   // (warp-uniform)
+                    }
+                    continue;
+                }
                 unsigned bk[kItemBatch][kChunk / 32], ps[kItemBatch][kChunk / 32];
 #pragma unroll
                 for (int k = 0; k < kItemBatch; k++) {
@@ -397,6 +423,14 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                             vp[q] = src_key;
                             if (e < len && st >= 0) vp[q] = __ldcs(P.packed + st + e);
                         }
+                        if (direct) {
+                            int v4[4];
+                            double a4[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) { v4[q] = base + BB * q < len ? vp[q] : kEmpty; a4[q] = add; }
+                            accum4(v4, a4, P.max_probe);
+                            continue;
+                        }
                         unsigned bk[4], ps[4];
 #pragma unroll
                         for (int q = 0; q < 4; q++) ps[q] = reserve(vp[q], base + BB * q < len, bk[q]);
@@ -406,7 +440,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 }
                 __syncthreads();
             }
-            if (tid == 0) { sm.n_push = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; }
+            if (tid == 0) { sm.n_push = 0; sm.n_edges = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; }
             GPB_PHASE(1);
             // ---------------------------------------------------------------- settle of level + 1, bucket by bucket
             const int nl = level + 1;
@@ -418,8 +452,8 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
             const double cand_thr = sm.tau_lb / (double)P.L * (1.0 - 1e-9);
             // A large level that arrives before any bound exists (a source with fewer than K neighbours whose neighbours have
             // thousands) would note every node: its candidates are picked from its log entries AFTER the level has set tau_lb.
-            unsigned level_pairs = 0;
-            for (int b = 0; b < P.nb; b++) level_pairs += s_cnt[b];
+            unsigned level_pairs = level_edges;
+            if (!direct) { level_pairs = 0; for (int b = 0; b < P.nb; b++) level_pairs += s_cnt[b]; }
             const bool defer = !P.full_merge && sm.tau_lb == 0.0 && level_pairs > 2048u;
             if (defer && tid < P.nb) s_lmark[tid] = min(s_lcnt[tid], (unsigned)P.capLog);
             long long lvl_max = 0;   // this thread's largest contribution of the level (a node of its own: a level's nodes are distinct)
@@ -427,14 +461,17 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 // one visit = consecutive buckets [b, e) whose pairs together cannot overfill the table (pairs bound the
                 // distinct nodes); a bucket above the limit is a visit of its own.  (s_cnt is stable since the barrier that
                 // ended the expansion, so every thread forms the same groups.)
-                unsigned tot = min(s_cnt[b], (unsigned)P.capPair);
-                int e = b + 1;
-                while (e < P.nb && tot + min(s_cnt[e], (unsigned)P.capPair) <= (unsigned)kGroupPairs) { tot += min(s_cnt[e], (unsigned)P.capPair); e++; }
-                if (tot == 0) { b = e; continue; }
+                int e = P.nb;   // (direct: the table already holds the whole level, one visit over all buckets)
+                if (!direct) {
+                    unsigned tot = min(s_cnt[b], (unsigned)P.capPair);
+                    e = b + 1;
+                    while (e < P.nb && tot + min(s_cnt[e], (unsigned)P.capPair) <= (unsigned)kGroupPairs) { tot += min(s_cnt[e], (unsigned)P.capPair); e++; }
+                    if (tot == 0) { b = e; continue; }
+                    for (int bb = b; bb < e; bb++)
+                        accumulate(pair_id + (long long)bb * P.capPair, pair_val + (long long)bb * P.capPair, min(s_cnt[bb], (unsigned)P.capPair), P.max_probe);
+                    __syncthreads();
+                }
                 const bool multi = e - b > 1;
-                for (int bb = b; bb < e; bb++)
-                    accumulate(pair_id + (long long)bb * P.capPair, pair_val + (long long)bb * P.capPair, min(s_cnt[bb], (unsigned)P.capPair), P.max_probe);
-                __syncthreads();
                 // settle: every thread scans its slots; reserve += coef * r (graph.h:90 / :106) goes to the log of the node's
                 // bucket (one counter update per warp and bucket), the push decision comes from the degree code in the key
 #pragma unroll 2
@@ -694,7 +731,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
         } else if (tid == 0) {
             P.redo[atomicAdd(P.redo_count, 1ull)] = (int)it; st_redo++; st_sources--;
         }
-        if (tid == 0) { sm.ovf = 0; sm.full = 0; sm.n_push = 0; sm.n_sel = 0; }
+        if (tid == 0) { sm.ovf = 0; sm.full = 0; sm.n_push = 0; sm.n_edges = 0; sm.n_sel = 0; }
         GPB_PHASE(4);
     }
     // counters
