@@ -45,7 +45,7 @@ struct Geo {
     static constexpr int SPT = kSlots / BB;               // table slots per thread in the scan
     static constexpr int kHashBits = BB == 1024 ? 12 : BB == 512 ? 11 : 10;   // log2(kBuckets4)
     static constexpr int kBigCap = BB == 1024 ? 32 : 8;
-    static constexpr int kListCap = BB == 1024 ? 1024 : BB * 3 / 4;   // push-list entries / top-k survivors kept in shared memory
+    static constexpr int kListCap = BB == 1024 ? 1024 : BB * 5 / 8;   // push-list entries / top-k survivors kept in shared memory
     static constexpr int kCandCap = BB;                   // push candidates of one table scan kept in shared memory
     static constexpr int kCandMax = kSlots / 2;           // nodes the candidate merge can hold in one table fill
     static constexpr int kGroupPairs = kSlots * 5 / 8;    // buckets are visited together while their pairs stay below this table load
@@ -114,6 +114,7 @@ struct BSmem {
     double add[Geo<BB>::kListCap];
     unsigned warp_scan[BB / 32 + 1];
     double wtau[BB / 32];
+    unsigned short wq[BB / 32][64];   // settle: per-warp queue of occupied table slots
     union {
         struct {   // top-k (block_topk): the histogram is dead once the boundary bucket is collected
             union {
@@ -472,64 +473,75 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                     __syncthreads();
                 }
                 const bool multi = e - b > 1;
-                // settle: every thread scans its slots; reserve += coef * r (graph.h:90 / :106) goes to the log of the node's
-                // bucket (one counter update per warp and bucket), the push decision comes from the degree code in the key
+                // settle: every thread scans its slots and the warp COMPACTS the occupied ones into a queue (a table filled to a
+                // third would otherwise walk the body below sixteen times per warp with a third of the lanes); 32 queued slots at
+                // a time: reserve += coef * r (graph.h:90 / :106) goes to the log of the node's bucket (one counter update per
+                // warp and bucket), the push decision comes from the degree code in the key, the slot is emptied
+                unsigned short *wq = sm.wq[tid >> 5];
+                int qn = 0;
+                auto settle32 = [&](const int off, const int cnt) {   // queue entries [off, off + cnt), cnt <= 32
+                    const bool have = lane < cnt;
+                    double rr = 0.0;
+                    unsigned key = 0u;
+                    if (have) {
+                        const int slot = wq[off + lane];
+                        rr = s_vals[slot]; key = (unsigned)s_keys[slot];
+                        s_vals[slot] = 0.0; s_keys[slot] = kEmpty;   // the table is empty again for the next visit
+                    }
+                    unsigned lb = (unsigned)b, pos;
+                    if (!multi) {
+                        unsigned base = 0;
+                        if (lane == 0) base = atomicAdd(&s_lcnt[b], (unsigned)cnt);
+                        pos = __shfl_sync(0xffffffffu, base, 0) + lane;
+                    } else {
+                        lb = have ? hash_node(key & idmask) >> bshift : 0xFFFFFFFFu;
+                        const unsigned peers = __match_any_sync(0xffffffffu, lb);
+                        const int leader = __ffs(peers) - 1;
+                        unsigned p0 = 0;
+                        if (have && lane == leader) p0 = atomicAdd(&s_lcnt[lb], (unsigned)__popc(peers));
+                        pos = __shfl_sync(0xffffffffu, p0, leader) + __popc(peers & ((1u << lane) - 1u));
+                    }
+                    if (have) {
+                        src_front++;
+                        const double cr = c * rr;
+                        if (pos < (unsigned)P.capLog) { const unsigned o = lb * capLog32 + pos; log_id[o] = (int)key; log_val[o] = cr; }
+                        else ovf = true;
+                        lvl_max = max(lvl_max, __double_as_longlong(cr));
+                        if (!defer && cr >= cand_thr) {   // (rare once the first two or three levels have set tau_lb)
+                            const int p = atomicAdd(&sm.n_cand, 1);
+                            if (p < capC) sup_id[p] = (int)key;
+                        }
+                        if (will_push) {
+                            const unsigned code = has_code ? key >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
+                            if (rr >= P.rmax * (double)code) {                       // necessary for graph.h:94; the exact test follows
+                                const int p = atomicAdd(&sm.n_sel, 1);
+                                if (p < kCandCap) { sm.cand.key[p] = key; sm.cand.r[p] = rr; }
+                                else consider(key, rr);
+                            }
+                        }
+                    }
+                };
+                const unsigned lt = (1u << lane) - 1u;
 #pragma unroll 2
                 for (int j = 0; j < SPT / 2; j++) {
                     const int slot = 2 * (j * BB + tid);
                     const double2 r2 = *reinterpret_cast<const double2 *>(s_vals + slot);
-                    const double rr[2] = {r2.x, r2.y};
-                    const bool got[2] = {r2.x != 0.0, r2.y != 0.0};
-                    const unsigned m0 = __ballot_sync(0xffffffffu, got[0]), m1 = __ballot_sync(0xffffffffu, got[1]);
-                    if (m0 | m1) {   // (warp-uniform)
-                        const int2 k2 = *reinterpret_cast<const int2 *>(s_keys + slot);
-                        const unsigned key[2] = {(unsigned)k2.x, (unsigned)k2.y};
-                        if (got[0] | got[1]) *reinterpret_cast<double2 *>(s_vals + slot) = make_double2(0.0, 0.0);
-                        unsigned lb[2] = {(unsigned)b, (unsigned)b}, pos[2];
-                        if (!multi) {
-                            // one counter update per warp: the first slots of all lanes, then the second slots
-                            unsigned base = 0;
-                            if (lane == 0) base = atomicAdd(&s_lcnt[b], (unsigned)(__popc(m0) + __popc(m1)));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            const unsigned lt = (1u << lane) - 1u;
-                            pos[0] = base + __popc(m0 & lt);
-                            pos[1] = base + __popc(m0) + __popc(m1 & lt);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 2; q++) {
-                                lb[q] = got[q] ? hash_node(key[q] & idmask) >> bshift : 0xFFFFFFFFu;
-                                const unsigned peers = __match_any_sync(0xffffffffu, lb[q]);
-                                const int leader = __ffs(peers) - 1;
-                                unsigned p0 = 0;
-                                if (got[q] && lane == leader) p0 = atomicAdd(&s_lcnt[lb[q]], (unsigned)__popc(peers));
-                                pos[q] = __shfl_sync(0xffffffffu, p0, leader) + __popc(peers & ((1u << lane) - 1u));
-                            }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            if (got[q]) {
-                                src_front++;
-                                const double cr = c * rr[q];
-                                if (pos[q] < (unsigned)P.capLog) { const unsigned o = lb[q] * capLog32 + pos[q]; log_id[o] = (int)key[q]; log_val[o] = cr; }
-                                else ovf = true;
-                                lvl_max = max(lvl_max, __double_as_longlong(cr));
-                                if (!defer && cr >= cand_thr) {   // (rare once the first two or three levels have set tau_lb)
-                                    const int p = atomicAdd(&sm.n_cand, 1);
-                                    if (p < capC) sup_id[p] = (int)key[q];
-                                }
-                                if (will_push) {
-                                    const unsigned code = has_code ? key[q] >> P.idbits : 0u;   // min(deg, cap): a lower bound of deg
-                                    if (rr[q] >= P.rmax * (double)code) {                       // necessary for graph.h:94; the exact test follows
-                                        const int p = atomicAdd(&sm.n_sel, 1);
-                                        if (p < kCandCap) { sm.cand.key[p] = key[q]; sm.cand.r[p] = rr[q]; }
-                                        else consider(key[q], rr[q]);
-                                    }
-                                }
-                            }
-                        }
-                        *reinterpret_cast<int2 *>(s_keys + slot) = make_int2(kEmpty, kEmpty);   // the table is empty again for the next visit
+                    const bool got0 = r2.x != 0.0, got1 = r2.y != 0.0;
+                    const unsigned m0 = __ballot_sync(0xffffffffu, got0), m1 = __ballot_sync(0xffffffffu, got1);
+                    if (m0) {   // (warp-uniform; qn < 32 here, the queue holds 64)
+                        if (got0) wq[qn + __popc(m0 & lt)] = (unsigned short)slot;
+                        qn += __popc(m0);
+                        __syncwarp();
+                        if (qn >= 32) { qn -= 32; settle32(qn, 32); __syncwarp(); }
+                    }
+                    if (m1) {
+                        if (got1) wq[qn + __popc(m1 & lt)] = (unsigned short)(slot + 1);
+                        qn += __popc(m1);
+                        __syncwarp();
+                        if (qn >= 32) { qn -= 32; settle32(qn, 32); __syncwarp(); }
                     }
                 }
+                if (qn) settle32(0, qn);
                 __syncthreads();
                 if (tid < e - b) s_cnt[b + tid] = 0;
                 if (tid == 0) sm.full = 0;
