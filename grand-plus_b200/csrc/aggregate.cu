@@ -20,7 +20,7 @@
 #include <algorithm>
 #include <string>
 
-extern int g_push_bucket, g_push_bucket_block, g_push_bucket_nb, g_push_bucket_merge, g_push_cluster, g_push_cluster_probe, g_push_hub_deg, g_push_max_clusters, g_push_smem_hash, g_push_smem_probe, g_push_max_ctas,
+extern int g_push_bucket, g_push_bucket_block, g_push_bucket_fill, g_push_bucket_nb, g_push_bucket_merge, g_push_cluster, g_push_cluster_probe, g_push_hub_deg, g_push_max_clusters, g_push_smem_hash, g_push_smem_probe, g_push_max_ctas,
     g_push_tuning_gen;  // gfpush.cu
 
 namespace {
@@ -790,6 +790,7 @@ int gp_set_tuning(const char *key, int64_t value) {
     }
     else if (k == "push_bucket_merge") { GP_REQUIRE(value == 0 || value == 1, "push_bucket_merge must be 0 (top-k candidates) or 1 (whole reserve)"); g_push_bucket_merge = (int)value; g_push_tuning_gen++; }
     else if (k == "push_bucket_block") { GP_REQUIRE(value == 0 || value == 256 || value == 512 || value == 1024, "push_bucket_block must be 0 (default), 256, 512 or 1024"); g_push_bucket_block = (int)value; g_push_tuning_gen++; }
+    else if (k == "push_bucket_fill") { GP_REQUIRE(value >= 3 && value <= 7, "push_bucket_fill must be in 3..7 (eighths of the table)"); g_push_bucket_fill = (int)value; }
     else if (k == "push_bucket_nb") { GP_REQUIRE(value >= 0 && value <= 256, "push_bucket_nb must be in 0..256 (0 = automatic)"); g_push_bucket_nb = (int)value; g_push_tuning_gen++; }
     else if (k == "push_bucket") { GP_REQUIRE(value >= 0 && value <= 2, "push_bucket must be 0 (off), 1 (auto) or 2 (always)"); g_push_bucket = (int)value; g_push_tuning_gen++; }
     else if (k == "push_cluster_probe") { GP_REQUIRE(value >= 1 && value <= 4096, "push_cluster_probe must be in [1, 4096]"); g_push_cluster_probe = (int)value; }

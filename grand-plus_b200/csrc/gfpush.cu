@@ -51,11 +51,13 @@ int g_push_cluster = 0;       // "push_cluster": the cluster kernel (gfpush_clus
 int g_push_cluster_probe = 128;   // "push_cluster_probe": 4-key buckets tried before a source is handed to the slab kernel
                                   // (at the loads the planner aims at the longest probe sequence is a few buckets)
 int g_push_hub_deg = 0;       // "push_hub_deg": entries of at least this degree are expanded by the whole cluster (0 = 64 x G)
-int g_push_bucket = 1;        // "push_bucket": the hash-bucket kernel (gfpush_bucket.cu) for supports far beyond shared memory:
-                              // 0 off, 1 auto (where the slab kernel would run), 2 always
+int g_push_bucket = 1;        // "push_bucket": the hash-bucket kernel (gfpush_bucket.cu), the default for every graph beyond the dense
+                              // shared-memory mode: 0 off (the shared-memory table tier / the slabs run), 1 auto (on unless
+                              // push_smem_hash = 2 asks for the table tier), 2 always
 int g_push_bucket_nb = 0;     // "push_bucket_nb": buckets per source (rounded up to a power of two); 0 = from the expected support
 int g_push_bucket_block = 0;  // "push_bucket_block": threads per CTA of the hash-bucket kernel: 1024 (one CTA per SM, 16 384-slot table), 512 (two per
-                              // SM, 8 192 slots each), 256 (three per SM, 4 096 slots); 0 = default
+                              // SM, 8 192 slots each), 256 (three per SM, 4 096 slots); 0 = from the expected support (plan_bucket)
+int g_push_bucket_fill = 5;   // "push_bucket_fill": eighths of the table one visit of the bucket kernel may fill with pushed edges (3..7)
 int g_push_bucket_merge = 0;  // "push_bucket_merge": 0 = merge only the top-k candidates (the support is not counted), 1 = merge the whole reserve
 int g_push_max_clusters = 0;  // "push_max_clusters": cap on the resident clusters (0 = all the device schedules); scaling experiments
 int g_push_max_ctas = 0;      // "push_max_ctas": cap on the persistent CTAs of gfpush_kernel (0 = all SMs); scaling experiments
@@ -828,6 +830,7 @@ struct gp_graph {
     // scratch (lazily sized for the most demanding call so far)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    size_t budget_cached = 0;   // half of the free device memory when it was last asked for (make_plan)
     long long scratch_ctas = 0, scratch_capF = 0, scratch_capS = 0;
     int scratch_mode = 0;
     int scratch_hslots = 0;
@@ -969,10 +972,12 @@ int make_plan(gp_graph *g, long long S, int L, double rmax, bool redo_only, Plan
         // cudaMemGetInfo takes the driver's allocation lock (0.2 - 6 ms per call measured inside a running pipeline): only
         // ask when the scratch the handle already holds does not cover this call
         if (g->scratch && bytes_for(ctas, &tmp) <= g->scratch_bytes) budget = g->scratch_bytes;
+        else if (g->budget_cached) budget = g->budget_cached;   // (asked once per allocation: ensure_scratch invalidates it)
         else {
             size_t free_b = 0, total_b = 0;
             GP_CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
             budget = (free_b + g->scratch_bytes) / 2;
+            g->budget_cached = budget;
         }
     }
     while (ctas > 1 && bytes_for(ctas, &tmp) > budget) ctas = std::max<long long>(1, ctas * 3 / 4);
@@ -998,6 +1003,7 @@ int ensure_scratch(gp_graph *g, const Plan &pl, long long S, cudaStream_t stream
     if (!g->scratch) {
         GP_CUDA_TRY(cudaMalloc(&g->scratch, pl.bytes));
         g->scratch_bytes = pl.bytes;
+        g->budget_cached = 0;   // the next plan that needs a budget asks the driver again
     }
     // table invariants between sources: next residue == 0 everywhere, reserve == kUnseen everywhere
     char *base = (char *)g->scratch;
@@ -1121,9 +1127,14 @@ struct BucketPlan {
 int plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, long long support_hint, BucketPlan *bp) {
     *bp = BucketPlan{};
     if (g_push_bucket == 0) return GP_OK;
-    if (g_push_bucket == 1 && pl.hslots > 0) return GP_OK;   // the shared-memory table tier takes this call
+    if (g_push_bucket == 1 && pl.hslots > 0 && g_push_smem_hash == 2) return GP_OK;   // the shared-memory table tier was asked for
     const long long n = g->n;
-    const int block = g_push_bucket_block ? g_push_bucket_block : kBucketDefaultBlock;
+    // Geometry (measured, profiles/r02_gfpush.md 6): supports of the order of one table (the regime the shared-memory table tier
+    // was built for: Reddit-, MAG-shape) run two sources per SM in 512-thread CTAs with 8 192-slot tables -- the barriers and
+    // dependent shared-memory round trips of one source overlap the other's; supports far beyond the table (Amazon2M-shape)
+    // keep one 1 024-thread CTA per SM with the 16 384-slot table (half the bucket visits per level).
+    const double est_support = rmax > 0.0 ? std::min(0.15 / rmax, (double)n) : (double)n;
+    const int block = g_push_bucket_block ? g_push_bucket_block : (est_support <= 2.0 * 16384.0 ? 512 : 1024);
     const long long slots = gpb_slots(block);
     // a level pushes at most min(nnz + n, 1/rmax) edges
     long long capE = g->nnz + n;
@@ -1316,6 +1327,8 @@ int push_device_locked(gp_graph *g, const int *d_node_idx, long long S, const do
             B.node_idx = d_node_idx; B.S = last; B.it_base = first; B.coef = g->d_coef; B.L = L; B.rmax = rmax; B.K = K;
             B.out_row = d_row; B.out_col = d_col; B.out_val = d_val; B.out_val32 = d_val32;
             B.pair_id = (int *)(bb + b.off_pi); B.pair_val = (double *)(bb + b.off_pv); B.capPair = b.capPair;
+            B.pair_stride = (long long)b.nb * b.capPair; B.log_stride = (long long)b.nb * b.capLog;
+            B.group_pairs = gpb_slots(b.block) * g_push_bucket_fill / 8;
             B.log_id = (int *)(bb + b.off_li); B.log_val = (double *)(bb + b.off_lv); B.capLog = b.capLog;
             B.push_start = (int *)(bb + b.off_ps); B.push_len = (int *)(bb + b.off_pl); B.push_add = (double *)(bb + b.off_pa);
             B.capP = b.capP;
@@ -1369,9 +1382,14 @@ int collect_stats(gp_graph *g, cudaStream_t stream) {
     unsigned long long h[9];
     GP_CUDA_TRY(cudaMemcpyAsync(h, g->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, stream));
     GP_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (g->last.bucket_count > 0 && h[8] > 0) {   // the largest support of the call sizes the buckets of the next one
-        const bool same = g->hint_L == g->cur_L && g->hint_rmax == g->cur_rmax;
-        g->support_hint = same ? std::max<long long>(g->support_hint, (long long)h[8]) : (long long)h[8];
+    if (g->last.bucket_count > 0 && h[8] > 0) {
+        // The buckets are sized from the largest support the PILOT saw.  A later call raises the measurement only when more
+        // than 2 % of its sources outgrew the table and were handed over: one hub source in ten thousand is cheaper on the
+        // slabs than twice the bucket visits for every source of every later call.
+        const bool same = g->support_hint > 0 && g->hint_L == g->cur_L && g->hint_rmax == g->cur_rmax;
+        const bool many_redone = (long long)h[6] * 50 > g->last.sources;
+        if (!same) g->support_hint = (long long)h[8];
+        else if (many_redone) g->support_hint = std::max<long long>(g->support_hint, (long long)h[8]);
         g->hint_L = g->cur_L; g->hint_rmax = g->cur_rmax;
     }
     g->last.edges_pushed = (int64_t)h[1];

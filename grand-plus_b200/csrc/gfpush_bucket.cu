@@ -48,7 +48,6 @@ struct Geo {
     static constexpr int kListCap = BB == 1024 ? 1024 : BB * 5 / 8;   // push-list entries / top-k survivors kept in shared memory
     static constexpr int kCandCap = BB;                   // push candidates of one table scan kept in shared memory
     static constexpr int kCandMax = kSlots / 2;           // nodes the candidate merge can hold in one table fill
-    static constexpr int kGroupPairs = kSlots * 5 / 8;    // buckets are visited together while their pairs stay below this table load
     static constexpr int kMinCtas = BB == 1024 ? 1 : BB == 512 ? 2 : 3;
 };
 
@@ -148,7 +147,8 @@ template <int BB>
 __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(const BucketPushParams P) {
     constexpr int kSlots = Geo<BB>::kSlots, kBuckets4 = Geo<BB>::kBuckets4, SPT = Geo<BB>::SPT, kHashBits = Geo<BB>::kHashBits;
     constexpr int kBigCap = Geo<BB>::kBigCap, kListCap = Geo<BB>::kListCap, kCandCap = Geo<BB>::kCandCap;
-    constexpr int kCandMax = Geo<BB>::kCandMax, kGroupPairs = Geo<BB>::kGroupPairs;
+    constexpr int kCandMax = Geo<BB>::kCandMax;
+    const int kGroupPairs = P.group_pairs;   // buckets are visited together while their pairs stay below this table load
     __shared__ BSmem<BB> sm;
     extern __shared__ __align__(16) double s_vals[];                                  // [kSlots] the bucket's residues / reserves
     int *s_keys = reinterpret_cast<int *>(s_vals + kSlots);             // [kSlots] packed node, kEmpty = free
@@ -162,10 +162,10 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
     const long long cta = blockIdx.x;
     const unsigned idmask = P.idbits >= 32 ? 0xFFFFFFFFu : ((1u << P.idbits) - 1u);
     const bool has_code = P.idbits < 32;
-    int *pair_id = P.pair_id + cta * P.nb * P.capPair;
-    double *pair_val = P.pair_val + cta * P.nb * P.capPair;
-    int *log_id = P.log_id + cta * P.nb * P.capLog;
-    double *log_val = P.log_val + cta * P.nb * P.capLog;
+    int *pair_id = P.pair_id + cta * P.pair_stride;
+    double *pair_val = P.pair_val + cta * P.pair_stride;
+    int *log_id = P.log_id + cta * P.log_stride;
+    double *log_val = P.log_val + cta * P.log_stride;
     int *push_start = P.push_start + cta * P.capP;
     int *push_len = P.push_len + cta * P.capP;
     double *push_add = P.push_add + cta * P.capP;

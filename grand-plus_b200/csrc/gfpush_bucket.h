@@ -18,6 +18,7 @@ struct BucketPushParams {
     int nb;                    // buckets = 2^log_nb (>= 2): bucket of a node = hash(node) >> (32 - log_nb)
     int log_nb;
     int max_probe;             // 4-key buckets of the table tried before the source is handed to the slab kernel
+    int group_pairs;           // consecutive buckets are one table fill while their pairs stay below this (default 5/8 of the slots)
     int full_merge;            // 1: merge the whole reserve (counts the support); 0: only the top-k candidates (default)
     const int *node_idx;
     long long S;               // sources [it_base, S) of node_idx are processed by this launch
@@ -34,9 +35,11 @@ struct BucketPushParams {
     int *pair_id;              // [ctas][nb][capPair]  pushed edges of the level, by bucket: packed node
     double *pair_val;          // [ctas][nb][capPair]  ... and the pushed amount r / deg
     long long capPair;
+    long long pair_stride;     // nb * capPair: one CTA's streams
     int *log_id;               // [ctas][nb][capLog]   reserve log of the source, by bucket: packed node
     double *log_val;           // [ctas][nb][capLog]   ... and coef * r
     long long capLog;
+    long long log_stride;      // nb * capLog
     int *push_start;           // [ctas][capP]  push list of the level beyond the entries kept in shared memory
     int *push_len;
     double *push_add;

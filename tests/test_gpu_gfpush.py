@@ -204,7 +204,7 @@ def test_gfpush_vs_live_reference_all_pubmed_sources():
 
 class _tuning:
     """Scoped gp_set_tuning: restores the defaults on exit."""
-    DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_bucket_block": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+    DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_bucket_block": 0, "push_bucket_fill": 5, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
                 "push_smem_probe": 2, "push_max_ctas": 0}
 
     def __init__(self, **kv):

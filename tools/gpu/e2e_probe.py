@@ -38,3 +38,5 @@ print("gfpush_omp, pinned host arrays     %.2f ms" % t(pinned))
 print("gfpush_omp, pageable numpy arrays  %.2f ms" % t(pageable))
 print("gfpush_device + 3 torch D2H copies %.2f ms" % t(dev_then_copy))
 print("gfpush_omp, pinned host arrays     %.2f ms" % t(pinned))
+for _ in range(3):
+    pinned(); print({k: graph.last_stats()[k] for k in ("bucket_count", "table_slots", "kernel_launches", "redo_sources", "ctas", "scratch_bytes")})

@@ -16,7 +16,7 @@ import bench  # noqa: E402
 from grandplus_b200 import _lib  # noqa: E402
 from grandplus_b200.precompute import propagation  # noqa: E402
 
-DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_bucket_block": 0, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
+DEFAULTS = {"push_bucket": 1, "push_bucket_merge": 0, "push_bucket_nb": 0, "push_bucket_block": 0, "push_bucket_fill": 5, "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_smem_hash": 1,
             "push_smem_probe": 2, "push_max_ctas": 0}
 
 
