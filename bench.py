@@ -118,7 +118,7 @@ class ClockSampler(threading.Thread):
         time.sleep(0.06)   # let the last periodic sample arrive
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for t, s in self.samples:
             if not any(t0 <= t <= t1 + 0.05 for t0, t1 in self.windows):
                 continue
@@ -129,10 +129,15 @@ class ClockSampler(threading.Thread):
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "sm_mhz_min": min(sm) if sm else None, "power_w_max": max(pw) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm),
                 "window": "device-timed steps + end-to-end steps (both under load)"}
 
@@ -481,12 +486,18 @@ def run_ours(args):
         for key, wl in (("config3_amazon2m", "amazon2m"), ("config4_mag", "mag")):
             if wl == args.workload:
                 continue
-            sr = measure_workload(wl, dev, rank, world, steps=3, warmup=3)
+            side_sampler = ClockSampler(local)   # (the side measurements run after the headline: their own clock samples)
+            side_sampler.start()
+            side_sampler.wait_first_sample()
+            sr = measure_workload(wl, dev, rank, world, steps=3, warmup=3, sampler=side_sampler)
+            side_clocks = side_sampler.stop()
+            side_clocks["window"] = "the side measurement's device-timed steps"
             line[key] = {"workload": f"BASELINE configs[{sr['w']['config']}] {wl}", "value": sr["value"], "unit": UNIT,
                          "ms_per_step": sr["step_time"] / sr["steps"] * 1e3, "steps": sr["steps"], "warmup": sr["warmup"],
                          "sources_per_step_per_gpu": sr["S"], "nodes": sr["n"], "csr_nnz": sr["nnz"], "rmax": sr["w"]["rmax"],
                          "order": sr["w"]["order"], "top_k": sr["K"], "features": sr["w"]["F"], "scaling": "weak",
-                         "roofline": sr["roof_push"], "roofline_aggregate": sr["roof_agg"], "setup_s": sr["setup_s"]}
+                         "roofline": sr["roof_push"], "roofline_aggregate": sr["roof_agg"], "setup_s": sr["setup_s"],
+                         "clocks": side_clocks}
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.workload, indptr_host, indices_host, n, budget_s=args.cpu_budget)
     if world > 1:
