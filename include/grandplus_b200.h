@@ -232,7 +232,9 @@ int gp_dropnode_mask(int64_t n_entries, int32_t n_aug, double p, uint64_t seed, 
  * 0 off, 1 auto from rmax, 2 always), "push_smem_probe" (4-key buckets tried before a node goes to the slab), "push_max_ctas"
  * (cap on persistent CTAs, for scaling experiments); the opt-in cluster kernel (one source per thread-block cluster):
  * "push_cluster" (0 off, 1 auto, -1 = one CTA, 2, 4, 8, 16 CTAs per source), "push_cluster_probe", "push_hub_deg",
- * "push_max_clusters"; "push_bucket" (the hash-bucket kernel: 0 off, 1 auto, 2 always), "push_bucket_nb" (buckets per source, 0 = automatic), "push_bucket_merge" (0 = the bucket kernel merges only the top-k candidates of a source and does not count its support, 1 = it merges the whole reserve).  The same keys are read from the GP_TUNING environment variable ("key=value,key=value") by the
+ * "push_max_clusters"; "push_bucket" (the hash-bucket kernel, the default beyond the dense shared-memory mode: 0 off, 1 auto, 2 always),
+ * "push_bucket_block" (threads per CTA: 1024 = one CTA per SM, 512 = two, 256 = three; 0 = from the expected support), "push_bucket_fill"
+ * (eighths of the table one visit may fill, 3..7), "push_bucket_nb" (buckets per source, 0 = automatic), "push_bucket_merge" (0 = the bucket kernel merges only the top-k candidates of a source and does not count its support, 1 = it merges the whole reserve).  The same keys are read from the GP_TUNING environment variable ("key=value,key=value") by the
  * Python loader. */
 int gp_set_tuning(const char *key, int64_t value);
 
