@@ -63,6 +63,27 @@ def test_product_package_never_imports_the_oracle():
                 assert "libgp_oracle" not in text and "oracle/_" not in text, f"{f} loads oracle binaries"
 
 
+def test_tuning_keys_are_validated_on_the_host():
+    """gp_set_tuning is pure host code: every documented key is accepted with its default, out-of-range values and
+    unknown keys are refused (the kernels never see an unchecked geometry)."""
+    from grandplus_b200 import _lib
+    defaults = {"push_bucket": 1, "push_bucket_block": 0, "push_bucket_fill": 5, "push_bucket_nb": 0, "push_bucket_merge": 0,
+                "push_cluster": 0, "push_cluster_probe": 128, "push_hub_deg": 0, "push_max_clusters": 0, "push_max_ctas": 0,
+                "push_smem_hash": 1, "push_smem_probe": 2}
+    for k, v in defaults.items():
+        _lib.set_tuning(k, v)
+    for k, bad in (("push_bucket_block", 384), ("push_bucket_block", 2048), ("push_bucket_fill", 8), ("push_bucket_fill", 2),
+                   ("push_bucket", 3), ("push_bucket_nb", 257), ("push_bucket_merge", 2), ("push_cluster", 3),
+                   ("push_smem_probe", 0), ("no_such_key", 1)):
+        with pytest.raises(_lib.GPError):
+            _lib.set_tuning(k, bad)
+    for geometry in (256, 512, 1024, 0):
+        _lib.set_tuning("push_bucket_block", geometry)
+    header = open(os.path.join(ROOT, "include", "grandplus_b200.h")).read()
+    for k in defaults:
+        assert f'"{k}"' in header, f"tuning key {k} is not documented in the header"
+
+
 def test_philox_known_answer():
     """Philox4x32-10 KATs from the Random123 distribution (kat_vectors): the DropNode masks are
     exactly reproducible from (seed, offset)."""
