@@ -138,7 +138,6 @@ struct BSmem {
     int sel_bin, sel_above, sel_inbin;
     int ovf;
     int full;                  // a probe sequence ran out: the source goes to the slab kernel, stop probing
-    double tau_lb;             // a lower bound of the source's K-th largest reserve, from the levels settled so far
     long long ph[8], t_prev;
 };
 
@@ -211,6 +210,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
         unsigned src_front = 0;
         unsigned long long src_edges = 0;
         bool ovf = false;
+        double tau_lb = 0.0;   // a lower bound of the source's K-th largest reserve, from the levels settled so far (uniform over the CTA)
 
         // A push-list entry {start, len, add = r / deg}, cut into chunks of kChunk edges (the unit one warp expands).
         auto add_entry = [&](int e_start, unsigned e_len, double e_add) {
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
             log_id[(long long)b0 * P.capLog] = src_key; log_val[(long long)b0 * P.capLog] = P.coef[0];
             s_lcnt[b0] = 1;
             src_front++;
-            sup_id[0] = src_key; sm.n_cand = 1; sm.tau_lb = 0.0;   // candidate merge (below): the source is a candidate
+            sup_id[0] = src_key; sm.n_cand = 1;   // candidate merge (below): the source is a candidate
         }
         __syncthreads();
         GPB_PHASE(0);
@@ -563,12 +563,12 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
             // Candidate merge (see the merge below): a node can only be among the K largest if ONE of its <= L contributions
             // coef * r is >= (K-th largest reserve) / L.  tau_lb is a lower bound of that reserve, so every contribution
             // >= tau_lb / L notes its node as a candidate (while tau_lb is 0: every node).
-            const double cand_thr = sm.tau_lb / (double)P.L * (1.0 - 1e-9);
+            const double cand_thr = tau_lb / (double)P.L * (1.0 - 1e-9);
             // A large level that arrives before any bound exists (a source with fewer than K neighbours whose neighbours have
             // thousands) would note every node: its candidates are picked from its log entries AFTER the level has set tau_lb.
             unsigned level_pairs = level_edges;
             if (!direct) { level_pairs = 0; for (int b = 0; b < P.nb; b++) level_pairs += s_cnt[b]; }
-            const bool defer = !P.full_merge && sm.tau_lb == 0.0 && level_pairs > 2048u;
+            const bool defer = !P.full_merge && tau_lb == 0.0 && level_pairs > 2048u;
             if (defer && tid < P.nb) s_lmark[tid] = min(s_lcnt[tid], (unsigned)P.capLog);
             long long lvl_max = 0;   // this thread's largest contribution of the level (a node of its own: a level's nodes are distinct)
             for (int b = 0; b < P.nb;) {
@@ -656,8 +656,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 }
                 if (qn) settle32(0, qn);
                 __syncthreads();
-                if (tid < e - b) s_cnt[b + tid] = 0;
-                if (tid == 0) sm.full = 0;
+                if (tid < e - b) s_cnt[b + tid] = 0;   // (sm.full stays set until the source ends: it is handed over anyway)
                 b = e;
             }
             __syncthreads();
@@ -670,10 +669,9 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 // tau_lb: the K-th largest of the threads' largest contributions of this level -- K different nodes whose
                 // reserve is at least that (a level's nodes are distinct, contributions only add up)
                 const double lvl_bound = block_kth_lower_bound<BB>(sm, P.K, lvl_max);   // (one histogram pass: within 1/32 of the K-th largest)
-                if (tid == 0 && lvl_bound > sm.tau_lb) sm.tau_lb = lvl_bound;
-                __syncthreads();
+                tau_lb = fmax(tau_lb, lvl_bound);   // (the same value in every thread: nothing to publish, no barrier)
                 if (defer) {   // this level's log entries (just written: L2) against the bound the level itself gave
-                    const double thr = sm.tau_lb / (double)P.L * (1.0 - 1e-9);
+                    const double thr = tau_lb / (double)P.L * (1.0 - 1e-9);
                     for (int b = 0; b < P.nb; b++) {
                         const unsigned hi = min(s_lcnt[b], (unsigned)P.capLog);
                         for (unsigned i = s_lmark[b] + tid; i < hi; i += BB) {
