@@ -1134,7 +1134,9 @@ int plan_bucket(gp_graph *g, long long S, int L, double rmax, const Plan &pl, lo
     // dependent shared-memory round trips of one source overlap the other's; supports far beyond the table (Amazon2M-shape)
     // keep one 1 024-thread CTA per SM with the 16 384-slot table (half the bucket visits per level).
     const double est_support = rmax > 0.0 ? std::min(0.15 / rmax, (double)n) : (double)n;
-    const int block = g_push_bucket_block ? g_push_bucket_block : (est_support <= 2.0 * 16384.0 ? 512 : 1024);
+    // (tiny supports -- rmax 1e-3 on the Reddit-shape graph: a few hundred nodes -- are pure latency chains: three sources per SM in
+    // 256-thread CTAs measured 21.4 M rows/s against 16.2 M at 512 threads and 6.8 M for the shared-memory-table kernel)
+    const int block = g_push_bucket_block ? g_push_bucket_block : est_support <= 512.0 ? 256 : est_support <= 2.0 * 16384.0 ? 512 : 1024;
     const long long slots = gpb_slots(block);
     // a level pushes at most min(nnz + n, 1/rmax) edges
     long long capE = g->nnz + n;

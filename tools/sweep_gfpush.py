@@ -34,7 +34,9 @@ def main():
         val = ctypes.c_size_t(0)
         rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
         print("L2 fetch granularity set rc", rc, "now", val.value, flush=True)
-    w = bench.WORKLOADS[name]
+    w = dict(bench.WORKLOADS[name])
+    if os.environ.get("SWEEP_RMAX"):
+        w["rmax"] = float(os.environ["SWEEP_RMAX"])
     S = int(os.environ.get("SWEEP_SOURCES", w["S"]))
     indptr, indices, n = bench.build_workload(name, dev)
     S = min(S, n)
