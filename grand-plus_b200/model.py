@@ -106,12 +106,37 @@ def narrow_index(idx: torch.Tensor, n_rows: int) -> torch.Tensor:
     return out
 
 
+MAX_AUG_PER_LAUNCH = 4   # one Philox block (four 32-bit words) per entry decides four augmentations
+
+
+def _chunk_offset(offset: int, c: int) -> int:
+    """Philox offset of the c-th group of four augmentations (c = 0: the caller's offset itself)."""
+    return (int(offset) + c * 0x9E3779B97F4A7C15) & (2**64 - 1)
+
+
+def _per_aug_group(A: int, mask, launch):
+    """The reference's --sample is unbounded (model.py:321); a launch handles four augmentations (one Philox block per
+    entry), so more are produced in groups of four with independent Philox offsets and concatenated.
+    ``launch(a, c, mask_group)`` -> (out [a,B,F], mask [a,nz] or None)."""
+    if A <= MAX_AUG_PER_LAUNCH:
+        return launch(A, 0, mask)
+    outs, masks = [], []
+    for c, a0 in enumerate(range(0, A, MAX_AUG_PER_LAUNCH)):
+        a = min(MAX_AUG_PER_LAUNCH, A - a0)
+        o, m = launch(a, c, None if mask is None else mask[a0:a0 + a].contiguous())
+        outs.append(o); masks.append(m)
+    return torch.cat(outs, 0), (torch.cat(masks, 0) if masks[0] is not None else None)
+
+
+
 def dropnode_mask(n_entries: int, n_aug: int, p: float, seed: int, offset: int, device) -> torch.Tensor:
     """The keep-mask gp_aggregate_fwd draws for (seed, offset): uint8 [n_aug, n_entries]."""
     lib = _lib.load()
     mask = torch.empty((n_aug, n_entries), dtype=torch.uint8, device=device)
-    _lib.check(lib.gp_dropnode_mask(int(n_entries), int(n_aug), float(p), int(seed) & (2**64 - 1),
-                                    int(offset) & (2**64 - 1), _vp(mask), _stream(mask.device)))
+    for c, a0 in enumerate(range(0, n_aug, MAX_AUG_PER_LAUNCH)):
+        a = min(MAX_AUG_PER_LAUNCH, n_aug - a0)
+        _lib.check(lib.gp_dropnode_mask(int(n_entries), int(a), float(p), int(seed) & (2**64 - 1),
+                                        _chunk_offset(offset, c), _vp(mask[a0:a0 + a]), _stream(mask.device)))
     return mask
 
 
@@ -237,8 +262,9 @@ def random_prop(feats, mat_scores, mat_idx, dropnode_rate, training=True, n_aug=
         seed, offset = st.seed, st.next()
     if mask is not None:
         mask = mask.to(torch.uint8).reshape(A, -1).contiguous()
-    out, m = _AggregateFn.apply(feats, int(feats.shape[1]), row_ptr, None, score, B, float(dropnode_rate),
-                                bool(training), A, seed, offset, mask, EPS_RANDOM_PROP, bool(return_mask))
+    out, m = _per_aug_group(A, mask, lambda a, c, mk: _AggregateFn.apply(
+        feats, int(feats.shape[1]), row_ptr, None, score, B, float(dropnode_rate), bool(training), a, seed,
+        _chunk_offset(offset, c), mk, EPS_RANDOM_PROP, bool(return_mask)))
     return _finish(out, m, n_aug, return_mask)
 
 
@@ -261,8 +287,9 @@ def random_prop_fused(features: DeviceFeatures, neighbor_idx, mat_scores, mat_id
         seed, offset = st.seed, st.next()
     if mask is not None:
         mask = mask.to(torch.uint8).reshape(A, -1).contiguous()
-    out, m = _AggregateFn.apply(features.data, features.F, row_ptr, nbr, score, B, float(dropnode_rate),
-                                bool(training), A, seed, offset, mask, EPS_RANDOM_PROP, bool(return_mask))
+    out, m = _per_aug_group(A, mask, lambda a, c, mk: _AggregateFn.apply(
+        features.data, features.F, row_ptr, nbr, score, B, float(dropnode_rate), bool(training), a, seed,
+        _chunk_offset(offset, c), mk, EPS_RANDOM_PROP, bool(return_mask)))
     return _finish(out, m, n_aug, return_mask)
 
 
@@ -372,9 +399,9 @@ def aggregate_slots(features: DeviceFeatures, col, val32, slot_rows=None, dropno
         seed, offset = st.seed, st.next()
     if mask is not None:
         mask = mask.to(torch.uint8).reshape(A, -1).contiguous()
-    out, m, _ = _launch_fwd(features.data, features.F, features.ld, None, slot_rows, K, col, val32, B, S * K,
-                            float(dropnode_rate), bool(training), A, seed, offset, mask, bool(return_mask),
-                            EPS_RANDOM_PROP, False)
+    out, m = _per_aug_group(A, mask, lambda a, c, mk: _launch_fwd(
+        features.data, features.F, features.ld, None, slot_rows, K, col, val32, B, S * K, float(dropnode_rate),
+        bool(training), a, seed, _chunk_offset(offset, c), mk, bool(return_mask), EPS_RANDOM_PROP, False)[:2])
     return _finish(out, m, n_aug, return_mask)
 
 

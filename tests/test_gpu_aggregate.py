@@ -117,6 +117,54 @@ def test_fused_gather_matches_oracle(Fdim, n_aug, agg_variant):
     assert np.all(out[:, 3] == 0)                            # empty row
 
 
+@pytest.mark.parametrize("n_aug", [5, 6, 9])
+def test_more_than_four_augmentations_run_in_groups(n_aug):
+    """The reference's --sample is unbounded (model.py:321): above four augmentations the launches are grouped, every
+    augmentation gets an independent mask, the masks are reproducible, and every augmentation matches the oracle --
+    through random_prop_fused, random_prop (with autograd) and aggregate_slots."""
+    import torch
+    from grandplus_b200 import model as gm
+    rng = np.random.default_rng(n_aug)
+    N, B, Fdim, K = 2000, 64, 37, 16
+    X = rng.standard_normal((N, Fdim)).astype(np.float32)
+    idx = np.repeat(np.arange(B), K).astype(np.int64)
+    nz = len(idx)
+    nbr = rng.integers(0, N, size=nz).astype(np.int64)
+    scores = (rng.random(nz) + 1e-3).astype(np.float32)
+    feats = gm.DeviceFeatures(X)
+    out, mask = gm.random_prop_fused(feats, torch.from_numpy(nbr).cuda(), torch.from_numpy(scores).cuda(),
+                                     torch.from_numpy(idx).cuda(), 0.5, training=True, n_aug=n_aug, seed=3, offset=9,
+                                     return_mask=True)
+    out, mask = out.cpu().numpy(), mask.cpu().numpy()
+    assert out.shape == (n_aug, B, Fdim) and mask.shape == (n_aug, nz)
+    np.testing.assert_array_equal(mask, gm.dropnode_mask(nz, n_aug, 0.5, 3, 9, "cuda").cpu().numpy())
+    for a in range(n_aug):
+        for b in range(a):
+            assert (mask[a] != mask[b]).mean() > 0.3          # pairwise independent, across the groups too
+        m = oa.dropout_scores(scores, 0.5, True, mask[a])
+        want64 = oa.random_prop(X[nbr], scores, idx, 0.5, True, mask[a], dtype=np.float64)
+        _assert_close(out[a], want64, _scale(X[nbr], m, idx))
+    # the reference's own signature on pre-gathered rows, importing the mask; gradient reaches every augmentation
+    f = torch.from_numpy(X[nbr]).cuda().requires_grad_(True)
+    o2 = gm.random_prop(f, torch.from_numpy(scores).cuda(), torch.from_numpy(idx).cuda(), 0.5, training=True, n_aug=n_aug,
+                        mask=torch.from_numpy(mask).cuda())
+    np.testing.assert_allclose(o2.detach().cpu().numpy(), out, rtol=1e-5, atol=1e-6)
+    w = torch.arange(1, n_aug + 1, device="cuda", dtype=torch.float32)[:, None, None]
+    (o2 * w).sum().backward()
+    g = f.grad.cpu().numpy()
+    want_g = np.zeros_like(g)
+    for a in range(n_aug):
+        m = oa.dropout_scores(scores, 0.5, True, mask[a]).astype(np.float64)
+        den = np.zeros(B); np.add.at(den, idx, m); den += 1e-12
+        want_g += (a + 1) * (m / den[idx])[:, None]
+    np.testing.assert_allclose(g, want_g, rtol=2e-4, atol=1e-6)
+    # GFPush slot layout
+    col = torch.from_numpy(nbr.reshape(B, K).astype(np.int32)).cuda()
+    val = torch.from_numpy(scores.reshape(B, K)).cuda()
+    o3 = gm.aggregate_slots(feats, col, val, None, 0.5, True, n_aug=n_aug, seed=3, offset=9)
+    np.testing.assert_allclose(o3.cpu().numpy(), out, rtol=1e-5, atol=1e-6)
+
+
 def test_eval_mode_ignores_mask_and_matches_oracle():
     import torch
     from grandplus_b200 import model as gm
