@@ -1,25 +1,34 @@
-// gfpush_bucket.cu -- GFPush + top-k for supports FAR beyond shared memory (Amazon2M-shape: 152 K nodes per source):
-// accumulate by HASH BUCKETS, one bucket at a time in a shared-memory table, instead of random read-modify-writes in HBM.
+// gfpush_bucket.cu -- GFPush + top-k for every graph beyond the dense shared-memory mode: accumulate by HASH BUCKETS, one
+// bucket at a time in a shared-memory table, instead of random read-modify-writes in HBM.
 // Same computation as gfpush.cu (Graph::gfpush_omp, /root/reference/precompute/graph.h:53-131), one CTA per source.
 //
 // The slab kernel (gfpush.cu MODE 0) touches one 16-byte slot per pushed edge and per settled node at a random HBM
 // address: a 64-byte fetch and a 32-byte write-back for 8 useful bytes, 62 MB of DRAM traffic per Amazon2M-shape source
 // (11 x the algorithmic bytes), bound by the DRAM random-access rate (profiles/r02_gfpush.md).  Here
 //   * expand APPENDS every pushed edge (packed node, r/deg) to the stream of the node's bucket, bucket = the top bits of
-//     hash(node) (nb = 2^k buckets, chosen so that a source's support per bucket fits the table at a load of ~0.6;
-//     one shared-memory counter per bucket; chunks of 128 edges per warp, coalesced CSR reads, no owner search);
-//   * a level is then settled bucket by bucket: the bucket's pairs are read back coalesced (thousands per visit, several per
-//     thread) and accumulated into a 16 384-slot open-addressed {key, residue} table in shared memory; every thread then
-//     scans its 16 slots: reserve += coef * r is appended to the bucket's reserve log, the push decision uses the degree
-//     code carried in the key (gfpush.cu) and fetches {start, degree} only for the few nodes that pass, and the slot is
-//     emptied for the next bucket;
-//   * after the last level the reserve logs are merged bucket by bucket through the same table into compact
-//     (node, reserve) arrays, from which the K largest are selected (threshold = the K-th largest lane maximum, then a
-//     radix select over the survivors; gfpush_shared.cuh).
-// All streams are written and read coalesced; nothing is read-modify-written in HBM.  (A first version used node-RANGE
-// buckets with a dense window: 150 buckets of ~1 000 pairs per level made every visit a 2 us latency chain for one pair per
-// thread, 70 K rows/s; profiles/r02_gfpush.md.)  A source whose bucket stream or table overflows is handed to the slab
-// kernel through the redo list.
+//     hash(node) (nb = 2^k buckets, chosen so that a source's support per bucket fits the table; one shared-memory
+//     counter per bucket).  Push-list entries are cut into chunks of 128 edges that one warp expands with four coalesced
+//     CSR reads per lane (no owner search); on levels of SHORT entries (low-degree graphs) a warp packs up to 32 entries:
+//     a scan of their lengths, then every lane finds the owner of its edge slot by a shuffle binary search;
+//   * a level is then settled bucket by bucket: the bucket's pairs are read back coalesced and accumulated into an
+//     open-addressed {key, residue} table in shared memory (4-key buckets, four pairs in flight per thread); the threads
+//     scan the table, compact the occupied slots into a per-warp queue and settle them 32 at a time: reserve += coef * r
+//     is appended to the bucket's reserve log, the push decision uses the degree code carried in the key (gfpush.cu) and
+//     fetches {start, degree} only for the few nodes that pass, the slot is emptied for the next visit.  A level whose
+//     pushed edges all fit ONE table fill skips the streams: expand accumulates straight into the table;
+//   * the reserve is merged for the TOP-K CANDIDATES only: a node can be among the K largest only if one of its <= L
+//     contributions is at least (K-th largest reserve) / L; a lower bound of that reserve is taken after every level (one
+//     histogram pass over the threads' largest contributions), and after the last level the logs stream once through a
+//     table that holds just the candidates.  The K largest are then selected as in gfpush.cu (gfpush_shared.cuh).
+// Because the table only ever holds one visit of one level and nodes keep no slot between levels, the table can be SMALL:
+// the kernel is a template over the CTA size with 16 table slots per thread -- 1024 threads (one CTA per SM, 16 384
+// slots) for supports far beyond shared memory, 512 threads (TWO sources per SM, 8 192 slots each) for supports of the
+// order of one table, 256 threads (three per SM) for tiny supports: the kernel is bound by barriers and dependent
+// shared-memory round trips, and a second source on the SM fills them (+23 % / +35 % over the shared-memory-table kernel
+// on the Reddit- / MAG-shape graphs).
+// All streams are written and read coalesced; nothing is read-modify-written in HBM.  A source whose bucket stream or
+// table overflows is handed to the slab kernel through the redo list.  Measured history, including the variants that
+// lost: profiles/r02_gfpush.md sections 5 and 7.
 #include "gfpush_bucket.h"
 #include "gfpush_shared.cuh"
 
