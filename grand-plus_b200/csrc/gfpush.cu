@@ -6,7 +6,14 @@
 //                  r^{i+1}[v] = sum_{u in N^-1(v), r^i[u] >= rmax deg(u)} r^i[u]/deg(u)  (+ dangling -> s)
 //                  reserve += coef[L-1] r^{L-1};  keep the top-K positive reserve entries.
 //
-// B200 design (not the reference's per-thread unordered_maps):
+// This file: the host side of GFPush (handles, planning, launches, stats, the C ABI) and gfpush_kernel, which is
+//   MODE 1 -- the DEFAULT for graphs whose dense residue array fits shared memory (Cora / Citeseer / Pubmed-sized),
+//   MODE 0 -- the slab kernel that takes the hand-overs of the first-pass kernels (and everything with push_bucket=0),
+//   MODE 2 -- the shared-memory-table tier, the default for table-sized supports until the hash-bucket kernel
+//             (gfpush_bucket.cu, two sources per SM) measured 23 - 35 % faster; kept behind push_bucket=0 / push_smem_hash=2.
+// Every graph beyond the dense mode runs gfpush_bucket.cu first (plan_bucket below).
+//
+// B200 design of gfpush_kernel (not the reference's per-thread unordered_maps):
 //   * persistent CTAs (SM count x resident CTAs), sources handed out through one global atomic
 //     counter -- the schedule(dynamic) of graph.h:73, so hub-heavy sources do not stall a wave;
 //   * the next-level residues of a source live ON CHIP whenever its support allows: a dense fp64 array in shared
