@@ -268,10 +268,13 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
             }
 #pragma unroll
             for (int q = 0; q < 4; q++) {
+                // a home bucket seen FULL of other keys stays that way (keys are final while the visit is live): probe on from
+                // the next bucket; after a lost claim the home bucket may still have a free slot: probe it again
+                unsigned first = ((unsigned)at[q] >> 2) + (st[q] == 3 ? 1u : 0u);
                 if (st[q] == 2 && won[q] != kEmpty && won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
                 if (st[q] == 3) {
                     bool claimed;
-                    at[q] = find_slot<kBuckets4>(s_keys, (unsigned)at[q] >> 2, vp[q], max_probe, claimed);
+                    at[q] = find_slot<kBuckets4>(s_keys, first & (kBuckets4 - 1), vp[q], max_probe, claimed);
                     if (at[q] < 0) { ovf = true; sm.full = 1; st[q] = 0; }
                 }
             }
