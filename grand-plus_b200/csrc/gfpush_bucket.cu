@@ -83,6 +83,58 @@ __device__ __forceinline__ int find_slot(int *keys, unsigned bucket, int vp, int
     return -1;
 }
 
+// Adds four pairs (v_q, a_q) into the table (graph.h:98 / :106); v_q == kEmpty: no pair.  Returns true when a probe sequence
+// ran out (the source is then handed to the slab kernel).  The kernel is bound by the latency of dependent shared-memory
+// operations, so every step runs for all four pairs before the next one: four key-bucket reads, four claims, four adds are in
+// flight together.  The home bucket settles ~9 of 10 pairs; the rest take find_slot.
+template <int kBuckets4, int kHashBits>
+__device__ __noinline__ bool accum4_fn(int *s_keys, double *s_vals, const unsigned idmask, const int bshift, const int max_probe,
+                                       const int v0, const int v1, const int v2, const int v3,
+                                       const double a0, const double a1, const double a2, const double a3) {
+    const int vp[4] = {v0, v1, v2, v3};
+    const double av[4] = {a0, a1, a2, a3};
+    bool overflow = false;
+    int at[4];     // slot of the key / of the first free slot in the home bucket
+    int st[4];     // 0 skip, 1 key found, 2 free slot to claim, 3 bucket holds other keys only
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1);
+        const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * hb);
+        const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
+        at[q] = 4 * (int)hb; st[q] = 3;
+#pragma unroll
+        for (int i = 3; i >= 0; i--) {   // (free slots are taken in index order: the first free one ends the search)
+            if (kk[i] == vp[q]) { st[q] = 1; at[q] = 4 * (int)hb + i; }
+            else if (kk[i] == kEmpty) { st[q] = 2; at[q] = 4 * (int)hb + i; }
+        }
+        if (vp[q] == kEmpty) st[q] = 0;
+    }
+    int won[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        won[q] = 0;
+        if (st[q] == 2) won[q] = atomicCAS(s_keys + at[q], kEmpty, vp[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        // a home bucket seen FULL of other keys stays that way (keys are final while the visit is live): probe on from
+        // the next bucket; after a lost claim the home bucket may still have a free slot: probe it again
+        unsigned first = ((unsigned)at[q] >> 2) + (st[q] == 3 ? 1u : 0u);
+        if (st[q] == 2 && won[q] != kEmpty && won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
+        if (st[q] == 3) {
+            bool claimed;
+            at[q] = find_slot<kBuckets4>(s_keys, first & (kBuckets4 - 1), vp[q], max_probe, claimed);
+            if (at[q] < 0) { overflow = true; st[q] = 0; }
+        }
+    }
+    // (atomicAdd on a shared-memory double is ptxas' ATOMS.CAST.SPIN loop; a hand-written compare-and-swap against
+    // 0.0 for freshly claimed slots measured SLOWER than leaving every add to it)
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        if (st[q] != 0) atomicAdd(s_vals + at[q], av[q]);
+    return overflow;
+}
+
 // The r-th largest of the lanes' values (bit patterns of non-negative doubles; 0 when fewer than r lanes hold a positive one).
 __device__ __forceinline__ long long warp_rth_largest(long long v, int r) {
     const int lane = threadIdx.x & 31;
@@ -240,49 +292,12 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
             if (d == 0) add_entry(-1, 1u, r);                                      // graph.h:91-93: back to the source
             else if (r >= P.rmax * (double)d) add_entry(rec.x, d, r / (double)d);   // graph.h:94-95
         };
-        // Adds the pairs (ids[i], vals[i]), i < n, into the table (graph.h:98 / :106).  The kernel is bound by the latency
-        // of dependent shared-memory operations (32 warps per SM, each find-or-claim + add is a chain of four), so a thread
-        // takes its pairs four at a time and runs every step for all four before the next one: four key-bucket reads, four
-        // claims, four adds are in flight together.  The home bucket settles ~9 of 10 pairs; the rest take find_slot.
         auto accum4 = [&](const int (&vp)[4], const double (&av)[4], const int max_probe) {   // (vp == kEmpty: no pair)
-            int at[4];     // slot of the key / of the first free slot in the home bucket
-            int st[4];     // 0 skip, 1 key found, 2 free slot to claim, 3 bucket holds other keys only
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const unsigned hb = (hash_node((unsigned)vp[q] & idmask) >> (bshift - kHashBits)) & (kBuckets4 - 1);
-                const int4 k4 = *reinterpret_cast<const int4 *>(s_keys + 4 * hb);
-                const int kk[4] = {k4.x, k4.y, k4.z, k4.w};
-                at[q] = 4 * (int)hb; st[q] = 3;
-#pragma unroll
-                for (int i = 3; i >= 0; i--) {   // (free slots are taken in index order: the first free one ends the search)
-                    if (kk[i] == vp[q]) { st[q] = 1; at[q] = 4 * (int)hb + i; }
-                    else if (kk[i] == kEmpty) { st[q] = 2; at[q] = 4 * (int)hb + i; }
-                }
-                if (vp[q] == kEmpty) st[q] = 0;
+            // (ONE copy of the find-or-claim + add code per kernel: inlined at its eight call sites it made a third of an
+            // 11 K-instruction kernel that stalls on instruction fetch)
+            if (accum4_fn<kBuckets4, kHashBits>(s_keys, s_vals, idmask, bshift, max_probe, vp[0], vp[1], vp[2], vp[3], av[0], av[1], av[2], av[3])) {
+                ovf = true; sm.full = 1;
             }
-            int won[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                won[q] = 0;
-                if (st[q] == 2) won[q] = atomicCAS(s_keys + at[q], kEmpty, vp[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                // a home bucket seen FULL of other keys stays that way (keys are final while the visit is live): probe on from
-                // the next bucket; after a lost claim the home bucket may still have a free slot: probe it again
-                unsigned first = ((unsigned)at[q] >> 2) + (st[q] == 3 ? 1u : 0u);
-                if (st[q] == 2 && won[q] != kEmpty && won[q] != vp[q]) st[q] = 3;   // somebody else took the slot for another node
-                if (st[q] == 3) {
-                    bool claimed;
-                    at[q] = find_slot<kBuckets4>(s_keys, first & (kBuckets4 - 1), vp[q], max_probe, claimed);
-                    if (at[q] < 0) { ovf = true; sm.full = 1; st[q] = 0; }
-                }
-            }
-            // (atomicAdd on a shared-memory double is ptxas' ATOMS.CAST.SPIN loop; a hand-written compare-and-swap against
-            // 0.0 for freshly claimed slots measured SLOWER than leaving every add to it)
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                if (st[q] != 0) atomicAdd(s_vals + at[q], av[q]);
         };
         auto accumulate = [&](const int *ids, const double *vals, const unsigned n, const int max_probe) {
             for (unsigned i0 = tid; i0 < n; i0 += BB * 4) {
