@@ -596,7 +596,12 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
             unsigned level_pairs = level_edges;
             if (!direct) { level_pairs = 0; for (int b = 0; b < P.nb; b++) level_pairs += s_cnt[b]; }
             const bool defer = !P.full_merge && tau_lb == 0.0 && level_pairs > 2048u;
-            if (defer && tid < P.nb) s_lmark[tid] = min(s_lcnt[tid], (unsigned)P.capLog);
+            if (defer) {   // (warp-uniform, rare)
+                if (tid < P.nb) s_lmark[tid] = min(s_lcnt[tid], (unsigned)P.capLog);
+                // a DIRECT level goes straight into the scan: without this barrier a fast warp appends to the logs before a slow
+                // thread has taken its mark, the deferred pick then skips those entries and their nodes never become candidates
+                __syncthreads();
+            }
             long long lvl_max = 0;   // this thread's largest contribution of the level (a node of its own: a level's nodes are distinct)
             for (int b = 0; b < P.nb;) {
                 // one visit = consecutive buckets [b, e) whose pairs together cannot overfill the table (pairs bound the
