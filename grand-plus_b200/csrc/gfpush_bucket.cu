@@ -549,6 +549,9 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 }
             }
             __syncthreads();
+            // (reset HERE, one barrier before the settle: a direct level enters its scan without another barrier, and the scan
+            // already counts into n_sel / the next push list)
+            if (tid == 0) { sm.n_push = 0; sm.n_edges = 0; sm.n_sel = 0; sm.next_item = 0; }
             {
                 const int n_big = min(sm.n_big, kBigCap);
                 for (int bi = 0; bi < n_big; bi++) {
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(BB, Geo<BB>::kMinCtas) gfpush_bucket_kernel(co
                 }
                 __syncthreads();
             }
-            if (tid == 0) { sm.n_push = 0; sm.n_edges = 0; sm.n_sel = 0; sm.next_item = 0; sm.n_big = 0; }
+            if (tid == 0) sm.n_big = 0;   // (only the next level's expansion touches it again)
             GPB_PHASE(1);
             // ---------------------------------------------------------------- settle of level + 1, bucket by bucket
             const int nl = level + 1;
